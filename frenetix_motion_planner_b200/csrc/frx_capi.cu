@@ -1,0 +1,461 @@
+// frx_capi.cu -- the C ABI (include/frx.h) over the sm_100a kernels.  Host C++ only; no torch types.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <new>
+#include <string>
+#include <vector>
+
+#include "frx.h"
+#include "frx_device.cuh"
+
+// launchers implemented in frx_kernels.cu
+size_t frx_eval_smem_bytes(int Mpad, int nchunk);
+cudaError_t frx_launch_eval(const FrxKernelArgs& a, int nchunk, int grid, cudaStream_t st);
+cudaError_t frx_eval_occupancy(int Mpad, int nchunk, int* blocks_per_sm);
+void frx_launch_obstacle_prep(int O, int T, int Tp, const double* pos, const double* cov, const double* theta,
+                              const double* hl, const double* hw, double* obs, cudaStream_t st);
+void frx_launch_static_prep(int B, const double* obb, double* out, cudaStream_t st);
+void frx_launch_argmin(const FrxBest* bb, int nblocks, FrxBest* out, cudaStream_t st);
+void frx_launch_collision_counter(long long N, const double* total, const uint32_t* flags, const FrxBest* winner,
+                                  unsigned long long* counters, int grid, cudaStream_t st);
+void frx_launch_gather(const double* states, long long N, int Ntp, const long long* idx, long long n_idx,
+                       uint32_t mask, double* out, cudaStream_t st);
+
+namespace {
+
+struct HostResult {
+    FrxBest winner;
+    unsigned long long counters[FRX_NUM_COUNTERS];
+};
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;   // elements
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, n * sizeof(T));
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+}  // namespace
+
+struct frx_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr, own_stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
+    std::string err;
+    int sm_count = 148;
+    int max_smem_optin = 0;
+
+    frx_params prm{};
+    bool have_params = false, have_ref = false, have_tables = false;
+    double kappa_max = 0.0;
+
+    DevBuf<double> ref; int M = 0, Mpad = 0;
+    DevBuf<double> Ttab; DevBuf<int> Tlen; DevBuf<double> tpow; int nT = 0, tpitch = 0;
+    DevBuf<double> obs, raw_pos, raw_cov, raw_theta, raw_hl, raw_hw; DevBuf<int> obs_len; int O = 0, T = 0, Tp = 0;
+    DevBuf<double> obs_pos; int n_obs_pos = 0;
+    DevBuf<double> sobb, raw_sobb; int B = 0;
+    DevBuf<double> sampling, grid;
+    DevBuf<double> states, costs, total; DevBuf<uint32_t> flags; DevBuf<int> traj_len;
+    DevBuf<FrxBest> blockbest, winner; DevBuf<unsigned long long> counters;
+    DevBuf<long long> gidx; DevBuf<double> gout;
+    HostResult* h_res = nullptr;
+
+    long long lastN = 0; int lastK = 0; int lastNtp = 0;
+    int occ_Mpad = -1, occ_nchunk = -1, occ_blocks = 1;
+};
+
+#define CK(call)                                                                       \
+    do {                                                                               \
+        cudaError_t e__ = (call);                                                      \
+        if (e__ != cudaSuccess) {                                                      \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__);            \
+            return (e__ == cudaErrorMemoryAllocation) ? FRX_ERR_NOMEM : FRX_ERR_CUDA;  \
+        }                                                                              \
+    } while (0)
+
+#define REQUIRE(cond, msg)        \
+    do {                          \
+        if (!(cond)) {            \
+            ctx->err = (msg);     \
+            return FRX_ERR_INVALID; \
+        }                         \
+    } while (0)
+
+static inline int nchunk_for(int Nt) { return (Nt + 31) / 32; }
+static inline int pitch_for(int Nt) { return (Nt + 3) & ~3; }
+
+extern "C" {
+
+int frx_abi_version(void) { return FRX_ABI_VERSION; }
+
+int frx_create(int device_ordinal, frx_ctx** out) {
+    if (!out) return FRX_ERR_INVALID;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device_ordinal < 0 || device_ordinal >= n)
+        return FRX_ERR_CUDA;   // no CUDA device: fail loudly, there is no CPU fallback
+    frx_ctx* ctx = new (std::nothrow) frx_ctx();
+    if (!ctx) return FRX_ERR_NOMEM;
+    ctx->device = device_ordinal;
+    if (cudaSetDevice(device_ordinal) != cudaSuccess) { delete ctx; return FRX_ERR_CUDA; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device_ordinal) != cudaSuccess) { delete ctx; return FRX_ERR_CUDA; }
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return FRX_ERR_CUDA; }
+    ctx->stream = ctx->own_stream;
+    cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1); cudaEventCreate(&ctx->evk0); cudaEventCreate(&ctx->evk1);
+    if (cudaMallocHost(&ctx->h_res, sizeof(HostResult)) != cudaSuccess) { frx_destroy(ctx); return FRX_ERR_NOMEM; }
+    if (ctx->winner.reserve(1) != cudaSuccess || ctx->counters.reserve(FRX_NUM_COUNTERS) != cudaSuccess) {
+        frx_destroy(ctx);
+        return FRX_ERR_NOMEM;
+    }
+    *out = ctx;
+    return FRX_OK;
+}
+
+int frx_destroy(frx_ctx* ctx) {
+    if (!ctx) return FRX_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
+    ctx->ref.release(); ctx->Ttab.release(); ctx->Tlen.release(); ctx->tpow.release();
+    ctx->obs.release(); ctx->raw_pos.release(); ctx->raw_cov.release(); ctx->raw_theta.release();
+    ctx->raw_hl.release(); ctx->raw_hw.release(); ctx->obs_len.release(); ctx->obs_pos.release();
+    ctx->sobb.release(); ctx->raw_sobb.release(); ctx->sampling.release(); ctx->grid.release();
+    ctx->states.release(); ctx->costs.release(); ctx->total.release(); ctx->flags.release(); ctx->traj_len.release();
+    ctx->blockbest.release(); ctx->winner.release(); ctx->counters.release(); ctx->gidx.release(); ctx->gout.release();
+    if (ctx->h_res) cudaFreeHost(ctx->h_res);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->evk0) cudaEventDestroy(ctx->evk0);
+    if (ctx->evk1) cudaEventDestroy(ctx->evk1);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+    return FRX_OK;
+}
+
+const char* frx_last_error(const frx_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int frx_set_stream(frx_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return FRX_ERR_INVALID;
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return FRX_OK;
+}
+
+int frx_synchronize(frx_ctx* ctx) {
+    if (!ctx) return FRX_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return FRX_OK;
+}
+
+int frx_set_reference(frx_ctx* ctx, int32_t M, const double* ref_pos, const double* ref_theta,
+                      const double* ref_curv, const double* ref_curv_d, const double* ref_x, const double* ref_y) {
+    if (!ctx) return FRX_ERR_INVALID;
+    REQUIRE(M >= 2 && ref_pos && ref_theta && ref_curv && ref_curv_d && ref_x && ref_y, "frx_set_reference: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    int Mpad = (M + 1) & ~1;
+    REQUIRE(frx_eval_smem_bytes(Mpad, 2) <= (size_t)ctx->max_smem_optin,
+            "frx_set_reference: reference path too long for the shared-memory table");
+    std::vector<double> h((size_t)6 * Mpad, 0.0);
+    const double* src[6] = {ref_pos, ref_theta, ref_curv, ref_curv_d, ref_x, ref_y};
+    for (int k = 0; k < 6; ++k) memcpy(h.data() + (size_t)k * Mpad, src[k], sizeof(double) * M);
+    CK(ctx->ref.reserve(h.size()));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpy(ctx->ref.p, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
+    ctx->M = M; ctx->Mpad = Mpad; ctx->have_ref = true;
+    return FRX_OK;
+}
+
+int frx_set_params(frx_ctx* ctx, const frx_params* p) {
+    if (!ctx) return FRX_ERR_INVALID;
+    REQUIRE(p != nullptr, "frx_set_params: null");
+    REQUIRE(p->N >= 1 && p->N <= 63, "frx_set_params: N must be in [1, 63]");
+    REQUIRE(p->dt > 0, "frx_set_params: dt must be > 0");
+    REQUIRE(p->n_costs >= 0 && p->n_costs <= FRX_MAX_COSTS, "frx_set_params: n_costs out of range");
+    for (int k = 0; k < p->n_costs; ++k)
+        REQUIRE(p->cost_ids[k] >= 0 && p->cost_ids[k] < FRX_NUM_COST_TERMS, "frx_set_params: unknown cost id");
+    if (ctx->have_params && ctx->prm.N != p->N) ctx->have_tables = false;
+    ctx->prm = *p;
+    ctx->kappa_max = tan(p->delta_max) / p->wheelbase;   // reactive_planner.py:492
+    ctx->have_params = true;
+    return FRX_OK;
+}
+
+int frx_set_time_tables(frx_ctx* ctx, int32_t nT, const double* T_values, const int32_t* traj_len, const double* tpow) {
+    if (!ctx) return FRX_ERR_INVALID;
+    REQUIRE(ctx->have_params, "frx_set_time_tables: call frx_set_params first");
+    REQUIRE(nT >= 1 && nT <= FRX_MAX_T_VALUES && T_values && traj_len && tpow, "frx_set_time_tables: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    const int Nt = ctx->prm.N + 1;
+    const int tpitch = nchunk_for(Nt) * 32;
+    for (int k = 0; k < nT; ++k)
+        REQUIRE(traj_len[k] >= 1 && traj_len[k] <= Nt, "frx_set_time_tables: traj_len exceeds the planning horizon");
+    std::vector<double> h((size_t)nT * 5 * tpitch, 0.0);
+    for (int k = 0; k < nT; ++k)
+        for (int p = 0; p < 5; ++p)
+            memcpy(h.data() + ((size_t)k * 5 + p) * tpitch, tpow + ((size_t)k * 5 + p) * Nt, sizeof(double) * Nt);
+    CK(ctx->Ttab.reserve(nT)); CK(ctx->Tlen.reserve(nT)); CK(ctx->tpow.reserve(h.size()));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpy(ctx->Ttab.p, T_values, sizeof(double) * nT, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->Tlen.p, traj_len, sizeof(int) * nT, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->tpow.p, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
+    ctx->nT = nT; ctx->tpitch = tpitch; ctx->have_tables = true;
+    return FRX_OK;
+}
+
+int frx_set_predictions(frx_ctx* ctx, int32_t O, int32_t T, const double* pos, const double* cov, const double* theta,
+                        const double* half_len, const double* half_wid, const int32_t* len_valid) {
+    if (!ctx) return FRX_ERR_INVALID;
+    if (O <= 0) { ctx->O = 0; return FRX_OK; }
+    REQUIRE(T >= 1 && pos && cov && theta && half_len && half_wid && len_valid, "frx_set_predictions: bad arguments");
+    for (int o = 0; o < O; ++o) REQUIRE(len_valid[o] >= 0 && len_valid[o] <= T, "frx_set_predictions: len_valid out of range");
+    CK(cudaSetDevice(ctx->device));
+    const int Tp = (T + 3) & ~3;
+    const size_t n = (size_t)O * T;
+    CK(ctx->raw_pos.reserve(n * 2)); CK(ctx->raw_cov.reserve(n * 4)); CK(ctx->raw_theta.reserve(n));
+    CK(ctx->raw_hl.reserve(O)); CK(ctx->raw_hw.reserve(O)); CK(ctx->obs_len.reserve(O));
+    CK(ctx->obs.reserve((size_t)O * FRX_OBS_NARR * Tp));
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemcpyAsync(ctx->raw_pos.p, pos, n * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->raw_cov.p, cov, n * 4 * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->raw_theta.p, theta, n * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->raw_hl.p, half_len, O * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->raw_hw.p, half_wid, O * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->obs_len.p, len_valid, O * sizeof(int), cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(ctx->obs.p, 0, (size_t)O * FRX_OBS_NARR * Tp * sizeof(double), st));
+    frx_launch_obstacle_prep(O, T, Tp, ctx->raw_pos.p, ctx->raw_cov.p, ctx->raw_theta.p, ctx->raw_hl.p, ctx->raw_hw.p,
+                             ctx->obs.p, st);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));   // host buffers may be pageable and reused by the caller
+    ctx->O = O; ctx->T = T; ctx->Tp = Tp;
+    return FRX_OK;
+}
+
+int frx_set_obstacle_positions(frx_ctx* ctx, int32_t n, const double* pos_xy) {
+    if (!ctx) return FRX_ERR_INVALID;
+    if (n <= 0) { ctx->n_obs_pos = 0; return FRX_OK; }
+    REQUIRE(pos_xy != nullptr, "frx_set_obstacle_positions: null");
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->obs_pos.reserve((size_t)n * 2));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpy(ctx->obs_pos.p, pos_xy, sizeof(double) * 2 * n, cudaMemcpyHostToDevice));
+    ctx->n_obs_pos = n;
+    return FRX_OK;
+}
+
+int frx_set_static_obbs(frx_ctx* ctx, int32_t B, const double* obb) {
+    if (!ctx) return FRX_ERR_INVALID;
+    if (B <= 0) { ctx->B = 0; return FRX_OK; }
+    REQUIRE(obb != nullptr, "frx_set_static_obbs: null");
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->raw_sobb.reserve((size_t)B * 5)); CK(ctx->sobb.reserve((size_t)B * 8));
+    CK(cudaMemcpyAsync(ctx->raw_sobb.p, obb, sizeof(double) * 5 * B, cudaMemcpyHostToDevice, ctx->stream));
+    frx_launch_static_prep(B, ctx->raw_sobb.p, ctx->sobb.p, ctx->stream);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->B = B;
+    return FRX_OK;
+}
+
+// common tail of the three plan entry points
+static int run_plan(frx_ctx* ctx, long long N, const double* d_sampling, bool grid_mode, int g_nv, int g_nd,
+                    const double* d_t1, const double* d_v1, const double* d_d1, const double* xcl,
+                    long long row_first, long long row_base, frx_result* out) {
+    REQUIRE(ctx->have_params && ctx->have_ref && ctx->have_tables,
+            "frx_plan: frx_set_params, frx_set_reference and frx_set_time_tables must be called first");
+    REQUIRE(out != nullptr, "frx_plan: null result");
+    const frx_params& p = ctx->prm;
+    const int Nt = p.N + 1, Ntp = pitch_for(Nt), nchunk = nchunk_for(Nt), K = p.n_costs;
+    cudaStream_t st = ctx->stream;
+    memset(out, 0, sizeof(*out));
+    out->argmin = -1; out->min_cost = INFINITY; out->n_rows = N;
+
+    if (p.store_states) CK(ctx->states.reserve((size_t)FRX_NUM_FIELDS * N * Ntp));
+    CK(ctx->costs.reserve((size_t)N * (K > 0 ? K : 1))); CK(ctx->total.reserve(N)); CK(ctx->flags.reserve(N));
+    CK(ctx->traj_len.reserve(N));
+
+    if (ctx->occ_Mpad != ctx->Mpad || ctx->occ_nchunk != nchunk) {
+        int b = 1;
+        CK(frx_eval_occupancy(ctx->Mpad, nchunk, &b));
+        REQUIRE(b >= 1, "frx_plan: eval kernel does not fit on an SM with this reference length");
+        ctx->occ_blocks = b; ctx->occ_Mpad = ctx->Mpad; ctx->occ_nchunk = nchunk;
+    }
+    long long want = (N + FRX_WARPS_PER_CTA - 1) / FRX_WARPS_PER_CTA;
+    long long full = (long long)ctx->sm_count * ctx->occ_blocks;
+    int grid = (int)(want < full ? want : full);
+    if (grid < 1) grid = 1;
+    CK(ctx->blockbest.reserve(grid));
+
+    FrxKernelArgs a;
+    memset(&a, 0, sizeof(a));
+    a.dt = p.dt; a.a_max = p.a_max; a.v_switch = p.v_switch; a.kappa_max = ctx->kappa_max; a.wb_rear = p.wb_rear_axle;
+    a.half_len = p.length / 2; a.half_wid = p.width / 2; a.x0_orientation = p.x0_orientation; a.v_des = p.desired_velocity;
+    for (int k = 0; k < K; ++k) { a.w[k] = p.cost_weights[k]; a.cost_ids[k] = p.cost_ids[k]; }
+    a.n_costs = K; a.Nt = Nt; a.Ntp = Ntp; a.low = p.low_vel_mode; a.draw = p.draw_traj_set; a.debug = p.kinematic_debug;
+    a.store_states = p.store_states; a.check_collisions = p.check_collisions;
+    a.ref = ctx->ref.p; a.M = ctx->M; a.Mpad = ctx->Mpad;
+    a.Ttab = ctx->Ttab.p; a.Tlen = ctx->Tlen.p; a.tpow = ctx->tpow.p; a.nT = ctx->nT; a.tpitch = ctx->tpitch;
+    a.obs = ctx->obs.p; a.obs_len = ctx->obs_len.p; a.O = ctx->O; a.Tp = ctx->Tp;
+    a.obs_pos = ctx->obs_pos.p; a.n_obs_pos = ctx->n_obs_pos; a.sobb = ctx->sobb.p; a.B = ctx->B;
+    a.sampling = grid_mode ? nullptr : d_sampling;
+    a.g_t1 = d_t1; a.g_v1 = d_v1; a.g_d1 = d_d1; a.g_nv = g_nv; a.g_nd = g_nd;
+    if (xcl) for (int k = 0; k < 6; ++k) a.xcl[k] = xcl[k];
+    a.row_first = row_first; a.row_base = row_base; a.N = N;
+    a.states = ctx->states.p; a.costs = ctx->costs.p; a.total = ctx->total.p; a.flags = ctx->flags.p;
+    a.traj_len = ctx->traj_len.p; a.blockbest = ctx->blockbest.p; a.counters = ctx->counters.p;
+
+    CK(cudaMemsetAsync(ctx->counters.p, 0, sizeof(unsigned long long) * FRX_NUM_COUNTERS, st));
+    CK(cudaEventRecord(ctx->evk0, st));
+    CK(frx_launch_eval(a, nchunk, grid, st));
+    CK(cudaEventRecord(ctx->evk1, st));
+    frx_launch_argmin(ctx->blockbest.p, grid, ctx->winner.p, st);
+    CK(cudaGetLastError());
+    if (p.check_collisions && (ctx->O > 0 || ctx->B > 0)) {
+        long long cg = (N + 255) / 256;
+        if (cg > (long long)ctx->sm_count * 4) cg = (long long)ctx->sm_count * 4;
+        frx_launch_collision_counter(N, ctx->total.p, ctx->flags.p, ctx->winner.p, ctx->counters.p, (int)cg, st);
+        CK(cudaGetLastError());
+    }
+    CK(cudaMemcpyAsync(&ctx->h_res->winner, ctx->winner.p, sizeof(FrxBest), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(ctx->h_res->counters, ctx->counters.p, sizeof(unsigned long long) * FRX_NUM_COUNTERS,
+                       cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(ctx->ev1, st));
+    CK(cudaStreamSynchronize(st));
+
+    ctx->lastN = N; ctx->lastK = K; ctx->lastNtp = Ntp;
+    const HostResult& h = *ctx->h_res;
+    if (h.counters[CNT_T_NOT_FOUND]) {
+        ctx->err = "frx_plan: a sampling row uses a duration (column 1) that is missing from frx_set_time_tables";
+        return FRX_ERR_INVALID;
+    }
+    out->argmin = (h.winner.idx >= 0) ? (h.winner.idx + row_base) : -1;
+    out->min_cost = (h.winner.idx >= 0) ? h.winner.cost : INFINITY;
+    out->n_in_list = (int64_t)h.counters[CNT_IN_LIST];
+    out->n_feasible = (int64_t)h.counters[CNT_FEASIBLE];
+    out->n_candidates = (int64_t)h.counters[CNT_CANDIDATES];
+    out->n_collide = (int64_t)h.counters[CNT_COLLIDE];
+    out->n_boundary = (int64_t)h.counters[CNT_BOUNDARY];
+    out->collision_counter = (int64_t)h.counters[CNT_COLLISION_COUNTER];
+    out->reason_counts[0] = (int64_t)h.counters[CNT_INFEASIBLE_IN_LIST];
+    for (int q = 1; q <= 10; ++q) out->reason_counts[q] = (int64_t)h.counters[CNT_REASON1 + q - 1];
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, ctx->evk0, ctx->evk1)); out->eval_kernel_ms = ms;
+    CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1)); out->total_device_ms = ms;
+    return FRX_OK;
+}
+
+int frx_plan(frx_ctx* ctx, int64_t N, const double* sampling, int64_t row_index_base, frx_result* out) {
+    if (!ctx) return FRX_ERR_INVALID;
+    REQUIRE(N >= 1 && sampling != nullptr, "frx_plan: empty sampling matrix");
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->sampling.reserve((size_t)N * 13));
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->sampling.p, sampling, (size_t)N * 13 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    return run_plan(ctx, N, ctx->sampling.p, false, 0, 0, nullptr, nullptr, nullptr, nullptr, 0, row_index_base, out);
+}
+
+int frx_plan_device(frx_ctx* ctx, int64_t N, const void* d_sampling, int64_t row_index_base, frx_result* out) {
+    if (!ctx) return FRX_ERR_INVALID;
+    REQUIRE(N >= 1 && d_sampling != nullptr, "frx_plan_device: empty sampling matrix");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    return run_plan(ctx, N, (const double*)d_sampling, false, 0, 0, nullptr, nullptr, nullptr, nullptr, 0, row_index_base, out);
+}
+
+int frx_plan_grid(frx_ctx* ctx, int32_t nt, const double* t1, int32_t nv, const double* ss1, int32_t nd,
+                  const double* d1, const double* x_cl, int64_t row_first, int64_t row_count, frx_result* out) {
+    if (!ctx) return FRX_ERR_INVALID;
+    REQUIRE(nt >= 1 && nv >= 1 && nd >= 1 && t1 && ss1 && d1 && x_cl, "frx_plan_grid: bad arguments");
+    const long long total = (long long)nt * nv * nd;
+    REQUIRE(row_first >= 0 && row_count >= 1 && row_first + row_count <= total, "frx_plan_grid: row range outside the grid");
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->grid.reserve((size_t)nt + nv + nd));
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->grid.p, t1, sizeof(double) * nt, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->grid.p + nt, ss1, sizeof(double) * nv, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->grid.p + nt + nv, d1, sizeof(double) * nd, cudaMemcpyHostToDevice, ctx->stream));
+    return run_plan(ctx, row_count, nullptr, true, nv, nd, ctx->grid.p, ctx->grid.p + nt, ctx->grid.p + nt + nv, x_cl,
+                    row_first, row_first, out);
+}
+
+int32_t frx_state_pitch(const frx_ctx* ctx) { return ctx ? ctx->lastNtp : 0; }
+
+int frx_get_states(frx_ctx* ctx, int64_t n_idx, const int64_t* idx, uint32_t field_mask, double* out) {
+    if (!ctx) return FRX_ERR_INVALID;
+    REQUIRE(ctx->lastN > 0 && ctx->prm.store_states, "frx_get_states: no materialised states (store_states = 0 or no plan yet)");
+    REQUIRE(n_idx >= 1 && idx && out && field_mask && field_mask < (1u << FRX_NUM_FIELDS), "frx_get_states: bad arguments");
+    for (int64_t k = 0; k < n_idx; ++k) REQUIRE(idx[k] >= 0 && idx[k] < ctx->lastN, "frx_get_states: row index out of range");
+    CK(cudaSetDevice(ctx->device));
+    const int nf = __builtin_popcount(field_mask);
+    const size_t n_out = (size_t)nf * n_idx * ctx->lastNtp;
+    CK(ctx->gidx.reserve(n_idx)); CK(ctx->gout.reserve(n_out));
+    CK(cudaMemcpyAsync(ctx->gidx.p, idx, sizeof(long long) * n_idx, cudaMemcpyHostToDevice, ctx->stream));
+    frx_launch_gather(ctx->states.p, ctx->lastN, ctx->lastNtp, ctx->gidx.p, n_idx, field_mask, ctx->gout.p, ctx->stream);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, ctx->gout.p, n_out * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return FRX_OK;
+}
+
+int frx_get_states_range(frx_ctx* ctx, int64_t first, int64_t count, uint32_t field_mask, double* out) {
+    if (!ctx) return FRX_ERR_INVALID;
+    REQUIRE(ctx->lastN > 0 && ctx->prm.store_states, "frx_get_states_range: no materialised states");
+    REQUIRE(first >= 0 && count >= 1 && first + count <= ctx->lastN && out && field_mask && field_mask < (1u << FRX_NUM_FIELDS),
+            "frx_get_states_range: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    const size_t rowb = (size_t)ctx->lastNtp * sizeof(double);
+    size_t fo = 0;
+    for (int f = 0; f < FRX_NUM_FIELDS; ++f) {
+        if (!(field_mask & (1u << f))) continue;
+        CK(cudaMemcpyAsync((char*)out + fo * count * rowb, ctx->states.p + ((size_t)f * ctx->lastN + first) * ctx->lastNtp,
+                           (size_t)count * rowb, cudaMemcpyDeviceToHost, ctx->stream));
+        ++fo;
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    return FRX_OK;
+}
+
+int frx_get_costs(frx_ctx* ctx, int64_t first, int64_t count, double* costs, double* total) {
+    if (!ctx) return FRX_ERR_INVALID;
+    REQUIRE(ctx->lastN > 0 && first >= 0 && count >= 1 && first + count <= ctx->lastN, "frx_get_costs: bad range");
+    CK(cudaSetDevice(ctx->device));
+    if (costs && ctx->lastK > 0)
+        CK(cudaMemcpyAsync(costs, ctx->costs.p + (size_t)first * ctx->lastK, sizeof(double) * count * ctx->lastK,
+                           cudaMemcpyDeviceToHost, ctx->stream));
+    if (total) CK(cudaMemcpyAsync(total, ctx->total.p + first, sizeof(double) * count, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return FRX_OK;
+}
+
+int frx_get_flags(frx_ctx* ctx, int64_t first, int64_t count, uint32_t* flags, int32_t* traj_len) {
+    if (!ctx) return FRX_ERR_INVALID;
+    REQUIRE(ctx->lastN > 0 && first >= 0 && count >= 1 && first + count <= ctx->lastN, "frx_get_flags: bad range");
+    CK(cudaSetDevice(ctx->device));
+    if (flags) CK(cudaMemcpyAsync(flags, ctx->flags.p + first, sizeof(uint32_t) * count, cudaMemcpyDeviceToHost, ctx->stream));
+    if (traj_len) CK(cudaMemcpyAsync(traj_len, ctx->traj_len.p + first, sizeof(int32_t) * count, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return FRX_OK;
+}
+
+int frx_device_pointers(frx_ctx* ctx, void** states, void** costs, void** total, void** flags) {
+    if (!ctx) return FRX_ERR_INVALID;
+    if (states) *states = ctx->states.p;
+    if (costs) *costs = ctx->costs.p;
+    if (total) *total = ctx->total.p;
+    if (flags) *flags = ctx->flags.p;
+    return FRX_OK;
+}
+
+}  // extern "C"

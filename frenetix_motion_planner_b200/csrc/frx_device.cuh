@@ -1,0 +1,73 @@
+// frx_device.cuh -- device-side data structures shared by the kernels and the C-ABI host code.
+#pragma once
+#include <stdint.h>
+#include "frx.h"
+
+#define FRX_WARPS_PER_CTA 4
+#define FRX_THREADS (FRX_WARPS_PER_CTA * 32)
+#define FRX_MAX_T_VALUES 128
+#define FRX_EPS 1e-5
+
+// obstacle table, SoA with step pitch Tp: arr[(o * FRX_OBS_NARR + k) * Tp + t]
+enum {
+    OB_PX = 0, OB_PY, OB_IV00, OB_IV01, OB_IV10, OB_IV11,           // mean + inverse covariance at step t
+    OB_HCX, OB_HCY, OB_HUX, OB_HUY, OB_HHA, OB_HHB, OB_HR,          // obb-sum hull of boxes t, t+1
+    FRX_OBS_NARR
+};
+
+// counters written by the eval kernel (unsigned long long each)
+enum {
+    CNT_IN_LIST = 0, CNT_FEASIBLE, CNT_CANDIDATES, CNT_COLLIDE, CNT_BOUNDARY, CNT_INFEASIBLE_IN_LIST,
+    CNT_REASON1,  // .. CNT_REASON1 + 9 = reason 10
+    CNT_COLLISION_COUNTER = CNT_REASON1 + 10,
+    CNT_T_NOT_FOUND,
+    FRX_NUM_COUNTERS
+};
+
+struct FrxBest {
+    double cost;
+    long long idx;
+};
+
+struct FrxKernelArgs {
+    // ---- scalars (frx_params, pre-digested on the host)
+    double dt, a_max, v_switch, kappa_max, wb_rear, half_len, half_wid, x0_orientation, v_des;
+    double w[FRX_MAX_COSTS];
+    int cost_ids[FRX_MAX_COSTS];
+    int n_costs;
+    int Nt, Ntp;            // samples per candidate, step pitch of the state tensor
+    int low, draw, debug;
+    int store_states, check_collisions;
+    // ---- reference path: 6 tables of Mpad doubles, contiguous (pos, theta, curv, curv_d, x, y)
+    const double* ref;
+    int M, Mpad;
+    // ---- time tables
+    const double* Ttab;     // [nT] distinct durations
+    const int* Tlen;        // [nT] traj_len
+    const double* tpow;     // [nT][5][tpitch]
+    int nT, tpitch;
+    // ---- predictions / obstacles
+    const double* obs;      // [O][FRX_OBS_NARR][Tp]
+    const int* obs_len;     // [O] valid steps
+    int O, Tp;
+    const double* obs_pos;  // [n_obs_pos][2] current obstacle positions (distance_to_obstacles)
+    int n_obs_pos;
+    const double* sobb;     // [B][8]: cx, cy, ux, uy, ha, hb, r, pad
+    int B;
+    // ---- candidates
+    const double* sampling; // [N][13] or nullptr (grid mode)
+    const double* g_t1; const double* g_v1; const double* g_d1;
+    int g_nv, g_nd;
+    double xcl[6];
+    long long row_first;    // global index of local row 0 (grid mode: also the first generated row)
+    long long row_base;     // added to the local index when reporting argmin
+    long long N;
+    // ---- outputs
+    double* states;         // [14][N][Ntp]
+    double* costs;          // [N][n_costs]
+    double* total;          // [N]
+    uint32_t* flags;        // [N]
+    int* traj_len;          // [N]
+    FrxBest* blockbest;     // [gridDim.x]
+    unsigned long long* counters;
+};

@@ -1,0 +1,170 @@
+/*
+ * frx.h -- C ABI of the B200 (sm_100a) reactive-planner hot path.
+ *
+ * One shared library, libfrx_b200.so, exports exactly the entry points below.  No C++ or torch
+ * types cross this boundary: plain pointers, sizes and POD structs only.  Every function returns
+ * FRX_OK (0) or a negative error code and never throws; frx_last_error() gives the message.
+ *
+ * What each entry point replaces in the reference (TUM-AVS/Frenetix-Motion-Planner):
+ *
+ *   frx_create / frx_destroy      frenetix.TrajectoryHandler(dt) life cycle
+ *                                 (frenetix_motion_planner/reactive_planner_cpp.py:49)
+ *   frx_set_reference             CoordinateSystem tables ref_pos/ref_theta/ref_curv/ref_curv_d
+ *                                 (cr_scenario_handler/utils/utils_coordinate_system.py:203-207) and
+ *                                 frenetix.CoordinateSystemWrapper(reference_path)
+ *                                 (reactive_planner_cpp.py:192)
+ *   frx_set_params                vehicle / planning / debug scalars read by check_feasibility
+ *                                 (frenetix_motion_planner/reactive_planner.py:274-577), the
+ *                                 add_feasability_function / add_cost_function set-up
+ *                                 (reactive_planner_cpp.py:96-141) and the name-sorted weight list of
+ *                                 AdaptableCostFunction (cost_functions/cost_function.py:55-60)
+ *   frx_set_time_tables           the rounded time-power tables of reactive_planner.py:296-300
+ *                                 (computed with numpy by the host layer, one per distinct duration)
+ *   frx_set_predictions           Planner.set_predictions / CalculateCollisionProbabilityFast set-up
+ *                                 (reactive_planner.py:49-51, reactive_planner_cpp.py:151-155) and
+ *                                 the obstacle side of collision_check_prediction
+ *                                 (cr_scenario_handler/utils/collision_check.py:110-200)
+ *   frx_set_obstacle_positions    CalculateDistanceToObstacleCost(positions) (reactive_planner_cpp.py:166)
+ *   frx_set_static_obbs           road-boundary collision objects (frenetix_motion_planner/planner.py:362-368)
+ *   frx_plan                      handler.generate_trajectories(sampling_matrix[N x 13], low_vel_mode) +
+ *                                 handler.evaluate_all_current_functions(True) +
+ *                                 get_sorted_trajectories()[0] after trajectory_collision_check
+ *                                 (reactive_planner_cpp.py:256,347-374; reactive_planner.py:89-94,184-272)
+ *   frx_plan_grid                 same, rows generated on the device from the three 1-D ranges that
+ *                                 generate_sampling_matrix would expand
+ *                                 (frenetix_motion_planner/sampling_matrix.py:85-121)
+ *   frx_plan_device               same as frx_plan with the sampling matrix already resident in HBM
+ *   frx_get_*                     lazy read-back of what the reference keeps in TrajectorySample objects
+ *                                 (frenetix_motion_planner/trajectories.py:56-478)
+ *
+ * Ownership: the caller owns every host buffer (row-major, float64 unless noted, may be pinned);
+ * the library owns all device buffers, valid until the next frx_plan* / frx_destroy on that ctx.
+ * Threading: one ctx = one CUDA stream; a ctx is NOT thread-safe; use one ctx per planner instance.
+ */
+#ifndef FRX_H
+#define FRX_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FRX_ABI_VERSION 1
+
+/* error codes */
+#define FRX_OK 0
+#define FRX_ERR_INVALID (-1)   /* bad argument / missing set-up call */
+#define FRX_ERR_CUDA (-2)      /* CUDA runtime error, see frx_last_error */
+#define FRX_ERR_NOMEM (-3)
+#define FRX_ERR_UNSUPPORTED (-4)
+
+/* state tensor fields: states[field][candidate][step], step pitch = frx_state_pitch() */
+enum {
+    FRX_F_X = 0, FRX_F_Y, FRX_F_THETA, FRX_F_V, FRX_F_A, FRX_F_KAPPA, FRX_F_KAPPA_DOT,
+    FRX_F_S, FRX_F_D, FRX_F_THETA_CL, FRX_F_S_DOT, FRX_F_S_DDOT, FRX_F_D_DOT, FRX_F_D_DDOT,
+    FRX_NUM_FIELDS
+};
+
+/* per-candidate flag bits */
+#define FRX_FLAG_VALID (1u << 0)
+#define FRX_FLAG_FEASIBLE (1u << 1)
+#define FRX_FLAG_REASON(r) (1u << (1 + (r))) /* r = 1..10: slots of _infeasible_count_kinematics */
+#define FRX_FLAG_COLLIDE (1u << 12)
+#define FRX_FLAG_BOUNDARY (1u << 13)
+#define FRX_FLAG_STORED (1u << 14)    /* has Cartesian/curvilinear samples (reactive_planner.py:551-567) */
+#define FRX_FLAG_IN_LIST (1u << 15)   /* member of trajectories_all */
+#define FRX_FLAG_COSTED (1u << 16)    /* cost function evaluated */
+#define FRX_FLAG_CANDIDATE (1u << 17) /* handed to the collision check / arg-min */
+
+/* cost term ids, alphabetical like the reference's evaluation order */
+enum {
+    FRX_COST_ACCELERATION = 0, FRX_COST_DISTANCE_TO_OBSTACLES, FRX_COST_DISTANCE_TO_REFERENCE_PATH,
+    FRX_COST_JERK, FRX_COST_LATERAL_JERK, FRX_COST_LONGITUDINAL_JERK, FRX_COST_ORIENTATION_OFFSET,
+    FRX_COST_PATH_LENGTH, FRX_COST_PREDICTION, FRX_COST_VELOCITY_OFFSET, FRX_NUM_COST_TERMS
+};
+#define FRX_MAX_COSTS 10
+
+typedef struct frx_ctx frx_ctx;
+
+typedef struct frx_params {
+    double dt;               /* planning.dt */
+    int32_t N;               /* int(horizon / dt); Nt = N + 1 samples per candidate; N <= 63 */
+    int32_t low_vel_mode;    /* Planner._LOW_VEL_MODE */
+    int32_t draw_traj_set;   /* debug.draw_traj_set */
+    int32_t kinematic_debug; /* debug.kinematic_debug */
+    double a_max, v_switch, delta_max, wheelbase, wb_rear_axle, length, width;
+    double x0_orientation;   /* x_0.orientation */
+    double desired_velocity;
+    int32_t n_costs;                       /* active cost terms, name-sorted */
+    int32_t cost_ids[FRX_MAX_COSTS];       /* FRX_COST_* */
+    double cost_weights[FRX_MAX_COSTS];
+    int32_t store_states;    /* 1: materialise states[14][N][pitch] in HBM (default) */
+    int32_t check_collisions;/* 1: OBB sweep vs predictions / static boxes for every candidate */
+} frx_params;
+
+typedef struct frx_result {
+    int64_t argmin;            /* global row index of the selected candidate, -1 if none */
+    double min_cost;           /* its total cost (+inf if none) */
+    int64_t n_rows;            /* rows evaluated by this call */
+    int64_t n_in_list;         /* len(trajectories_all) */
+    int64_t n_feasible;        /* valid and feasible members of the list */
+    int64_t n_candidates;      /* handed to the collision check */
+    int64_t n_collide;         /* candidates overlapping a predicted obstacle */
+    int64_t n_boundary;        /* candidates overlapping a static box */
+    int64_t collision_counter; /* colliding candidates the lazy reference loop would have visited */
+    int64_t reason_counts[11]; /* _infeasible_count_kinematics (slot 0 = infeasible-or-invalid in list) */
+    float eval_kernel_ms;      /* device time of the eval kernel (CUDA events on the ctx stream) */
+    float total_device_ms;     /* first H2D to last D2H of this call, CUDA events */
+} frx_result;
+
+int frx_abi_version(void);
+int frx_create(int device_ordinal, frx_ctx** out);
+int frx_destroy(frx_ctx* ctx);
+const char* frx_last_error(const frx_ctx* ctx);
+
+int frx_set_reference(frx_ctx* ctx, int32_t M, const double* ref_pos, const double* ref_theta,
+                      const double* ref_curv, const double* ref_curv_d, const double* ref_x,
+                      const double* ref_y);
+int frx_set_params(frx_ctx* ctx, const frx_params* p);
+/* nT distinct durations; traj_len[k] samples are valid for T_values[k]; tpow[k][p][i] (p = 0..4 for
+ * t, t^2 .. t^5; i < Nt) row-major [nT][5][Nt] */
+int frx_set_time_tables(frx_ctx* ctx, int32_t nT, const double* T_values, const int32_t* traj_len,
+                        const double* tpow);
+/* O obstacles x T steps: pos [O][T][2], cov [O][T][2][2], theta [O][T]; half_len/half_wid [O];
+ * len_valid[O] = number of valid steps (<= T).  O = 0 clears. */
+int frx_set_predictions(frx_ctx* ctx, int32_t O, int32_t T, const double* pos, const double* cov,
+                        const double* theta, const double* half_len, const double* half_wid,
+                        const int32_t* len_valid);
+int frx_set_obstacle_positions(frx_ctx* ctx, int32_t n, const double* pos_xy);
+/* B boxes [B][5] = cx, cy, theta, half_len, half_wid.  B = 0 clears. */
+int frx_set_static_obbs(frx_ctx* ctx, int32_t B, const double* obb);
+
+/* rows: host [N][13] = t0,t1,s0,ss0,sss0,ss1,sss1,d0,dd0,ddd0,d1,dd1,ddd1.  row_index_base is
+ * added to local row numbers in frx_result.argmin (shards of a larger matrix). */
+int frx_plan(frx_ctx* ctx, int64_t N, const double* sampling, int64_t row_index_base, frx_result* out);
+/* same, sampling already in device memory (pointer from cudaMalloc / torch) */
+int frx_plan_device(frx_ctx* ctx, int64_t N, const void* d_sampling, int64_t row_index_base,
+                    frx_result* out);
+/* rows generated on device in itertools.product order (t1 slowest, then ss1, then d1);
+ * x_cl = s0,ss0,sss0,d0,dd0,ddd0; evaluates global rows [row_first, row_first + row_count) */
+int frx_plan_grid(frx_ctx* ctx, int32_t nt, const double* t1, int32_t nv, const double* ss1,
+                  int32_t nd, const double* d1, const double* x_cl, int64_t row_first,
+                  int64_t row_count, frx_result* out);
+
+/* read-back (rows are LOCAL indices of the last plan call) */
+int32_t frx_state_pitch(const frx_ctx* ctx);
+int frx_get_states(frx_ctx* ctx, int64_t n_idx, const int64_t* idx, uint32_t field_mask, double* out);
+int frx_get_states_range(frx_ctx* ctx, int64_t first, int64_t count, uint32_t field_mask, double* out);
+int frx_get_costs(frx_ctx* ctx, int64_t first, int64_t count, double* costs, double* total);
+int frx_get_flags(frx_ctx* ctx, int64_t first, int64_t count, uint32_t* flags, int32_t* traj_len);
+/* raw device pointers of the last plan (states, costs, total, flags) for zero-copy consumers */
+int frx_device_pointers(frx_ctx* ctx, void** states, void** costs, void** total, void** flags);
+/* use an externally created stream (e.g. torch's current stream); 0 restores the private stream */
+int frx_set_stream(frx_ctx* ctx, void* cuda_stream);
+int frx_synchronize(frx_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FRX_H */

@@ -361,6 +361,20 @@ def check_feasibility_one(row, ref: RefPath, prm: Params):
     feasible = True
     valid = True
     out = dict(c_lon=c_lon, c_lat=c_lat)
+    # distance of every data-dependent DECISION to its threshold (SURVEY.md 4.5 "margin protocol"):
+    # candidates whose smallest margin is ~1 ulp sit on a structural tie (e.g. a velocity profile
+    # constructed to end at exactly 0.001 m/s, the `> 0.001` stand-still threshold) whose outcome
+    # depends on LAPACK rounding noise even in the reference itself.
+    margin = [np.inf]
+
+    def upd(m):
+        m = np.min(np.abs(np.asarray(m, dtype=float))) if np.size(m) else np.inf
+        if np.isnan(m):
+            m = 0.0
+        if m < margin[0]:
+            margin[0] = float(m)
+    if prm.low_vel_mode:
+        upd(evaluate_position_at_tau(c_lon, t1, t1) - s0)
 
     # ---- :296-303
     t, t2, t3, t4, t5 = time_grid(t1, dT)
@@ -410,9 +424,13 @@ def check_feasibility_one(row, ref: RefPath, prm: Params):
             fl |= FLAG_IN_LIST
         if stored:
             fl |= FLAG_STORED
-        out.update(state=state, flags=fl, reasons=reasons, feasible=feasible, valid=valid)
+        out.update(state=state, flags=fl, reasons=reasons, feasible=feasible, valid=valid, margin=margin[0])
         return out
 
+    upd(s_velocity + _EPS)
+    upd(np.abs(s_velocity) - _EPS)
+    if not prm.draw_traj_set:
+        upd(np.abs(s_acceleration) - prm.a_max)
     # ---- :350-355
     if np.any(s_velocity < -_EPS):
         valid = False
@@ -442,6 +460,7 @@ def check_feasibility_one(row, ref: RefPath, prm: Params):
     with np.errstate(all="ignore"):
         for i in range(0, Nt):
             if not prm.low_vel_mode:
+                upd(s_velocity[i] - 0.001)
                 if s_velocity[i] > 0.001:
                     dp = d_velocity[i] / s_velocity[i]
                 else:
@@ -488,6 +507,7 @@ def check_feasibility_one(row, ref: RefPath, prm: Params):
                     oneKrD * tanTheta * (kappa_gl[i] * (oneKrD / cosTheta) - k_r) - (
                     k_r_d * d[i] + k_r * dp))
 
+            upd(v[i] + _EPS)
             if v[i] < -_EPS:
                 feasible = False
                 reasons[4] = 1
@@ -495,6 +515,7 @@ def check_feasibility_one(row, ref: RefPath, prm: Params):
                     break
 
             kappa_max = np.tan(prm.delta_max) / prm.wheelbase
+            upd(abs(kappa_gl[i]) - kappa_max)
             if abs(kappa_gl[i]) > kappa_max:
                 feasible = False
                 reasons[5] = 1
@@ -503,6 +524,8 @@ def check_feasibility_one(row, ref: RefPath, prm: Params):
 
             yaw_rate = (theta_gl[i] - theta_gl[i - 1]) / dT if i > 0 else 0.
             theta_dot_max = kappa_max * v[i]
+            if not (abs(round(yaw_rate, 5)) == 0 and theta_dot_max == 0):   # exact 0 > 0 is reproducible
+                upd(abs(round(yaw_rate, 5)) - theta_dot_max)
             if abs(round(yaw_rate, 5)) > theta_dot_max:
                 feasible = False
                 reasons[6] = 1
@@ -510,6 +533,7 @@ def check_feasibility_one(row, ref: RefPath, prm: Params):
                     break
 
             kappa_dot = (kappa_gl[i] - kappa_gl[i - 1]) / dT if i > 0 else 0.
+            upd(abs(kappa_dot) - 0.4)
             if abs(kappa_dot) > 0.4:
                 feasible = False
                 reasons[7] = 1
@@ -519,6 +543,8 @@ def check_feasibility_one(row, ref: RefPath, prm: Params):
             v_switch = prm.v_switch
             a_max = prm.a_max * v_switch / v[i] if v[i] > v_switch else prm.a_max
             a_min = -prm.a_max
+            upd(a[i] - a_max)
+            upd(a[i] - a_min)
             if not a_min <= a[i] <= a_max:
                 feasible = False
                 reasons[8] = 1
@@ -527,6 +553,8 @@ def check_feasibility_one(row, ref: RefPath, prm: Params):
 
     # ---- :536-567
     stored = False
+    upd(s - ref_pos[0])
+    upd(s - ref_pos[-1])
     if feasible or prm.draw_traj_set:
         for i in range(0, Nt):
             pos = ccosy_to_cartesian(ref, s[i], d[i])
@@ -612,6 +640,7 @@ def plan(sampling: np.ndarray, ref: RefPath, prm: Params, predictions: Sequence[
     costs = np.zeros((n, K))
     total = np.zeros(n)
     coeffs = np.zeros((n, 12))
+    margins = np.zeros(n)
     reason_counts = np.zeros(11)
 
     for r in range(n):
@@ -621,6 +650,7 @@ def plan(sampling: np.ndarray, ref: RefPath, prm: Params, predictions: Sequence[
         traj_len[r] = o["traj_len"]
         coeffs[r, :6] = o["c_lon"]
         coeffs[r, 6:] = o["c_lat"]
+        margins[r] = o["margin"]
         reason_counts += o["reasons"]
 
     valid = (flags & FLAG_VALID) != 0
@@ -671,7 +701,7 @@ def plan(sampling: np.ndarray, ref: RefPath, prm: Params, predictions: Sequence[
                 if not check_all_collisions:
                     break
     return dict(states=states, flags=flags, traj_len=traj_len, costs=costs, total=total,
-                coeffs=coeffs, reason_counts=reason_counts, n_in_list=n_list, n_feasible=n_feasible,
+                coeffs=coeffs, margins=margins, reason_counts=reason_counts, n_in_list=n_list, n_feasible=n_feasible,
                 percentage=percentage, argmin=winner,
                 min_cost=(float(total[winner]) if winner >= 0 else float("inf")),
                 collision_counter=collision_counter, cost_names=names)

@@ -45,3 +45,93 @@ def rel_err(a, b):
     e = np.where(np.isnan(a) & np.isnan(b), 0.0, e)
     e = np.where(np.isinf(a) & np.isinf(b) & (np.sign(a) == np.sign(b)), 0.0, e)
     return float(np.max(e)) if e.size else 0.0
+
+
+# ---------------------------------------------------------------------------------------------
+# device side (through the C ABI)
+# ---------------------------------------------------------------------------------------------
+def configure_handler(h, ref, prm, preds, static_obbs=None, sampling=None, T_values=None,
+                      store_states=True, check_collisions=True):
+    from frenetix_motion_planner_b200 import hotpath
+    names = prm.active_costs()
+    h.set_params(dt=prm.dt, N=prm.N, low_vel_mode=prm.low_vel_mode, draw_traj_set=prm.draw_traj_set,
+                 kinematic_debug=prm.kinematic_debug, a_max=prm.a_max, v_switch=prm.v_switch,
+                 delta_max=prm.delta_max, wheelbase=prm.wheelbase, wb_rear_axle=prm.wb_rear_axle,
+                 length=prm.length, width=prm.width, x0_orientation=prm.x0_orientation,
+                 desired_velocity=prm.desired_velocity, cost_names=names,
+                 cost_weights=[prm.cost_weights[n] for n in names], store_states=store_states,
+                 check_collisions=check_collisions)
+    h.set_reference(ref.ref_pos, ref.ref_theta, ref.ref_curv, ref.ref_curv_d, ref.ref_x, ref.ref_y)
+    if T_values is None:
+        T_values = hotpath.distinct_durations(sampling)
+    h.set_time_tables(*hotpath.time_tables(T_values, prm.dt, prm.N + 1))
+    packed = hotpath.pack_predictions(list(preds)) if preds else None
+    if packed is None:
+        h.set_predictions(None, None, None, [], [], [])
+    else:
+        h.set_predictions(*packed)
+    h.set_obstacle_positions(prm.obstacle_positions)
+    h.set_static_obbs(static_obbs)
+
+
+def device_plan(sampling, ref, prm, preds, static_obbs=None, device=0, handler=None, **kw):
+    """Run one plan through libfrx_b200 and read everything back (test use: small N)."""
+    from frenetix_motion_planner_b200 import _capi
+    h = handler or _capi.Handler(device)
+    configure_handler(h, ref, prm, preds, static_obbs, sampling=sampling, **kw)
+    res = h.plan(np.ascontiguousarray(sampling, dtype=np.float64))
+    flags, traj_len = h.get_flags()
+    costs, total = h.get_costs()
+    states = h.get_states_range() if kw.get("store_states", True) else None
+    out = dict(res=res, flags=flags, traj_len=traj_len, costs=costs, total=total, states=states,
+               argmin=int(res.argmin), min_cost=float(res.min_cost),
+               reason_counts=np.array(list(res.reason_counts), dtype=np.int64),
+               n_in_list=int(res.n_in_list), n_feasible=int(res.n_feasible),
+               collision_counter=int(res.collision_counter), handler=h)
+    return out
+
+
+BAND = 1e-9   # decision margin below which the reference's own outcome is rounding noise
+
+
+def compare_with_oracle(dev, ora, prm, tol=1e-6, check_collide=True, band=BAND):
+    """Assert the parity contract: masks / selected index bit-exact, states & costs within `tol`
+    relative -- for every candidate whose decision margins exceed `band`; the rest
+    sit on structural ties of the reference (see oracle docstring) and are only counted."""
+    from oracle import frenet_oracle as fo
+    ok = ora["margins"] >= band if "margins" in ora else np.ones(len(ora["flags"]), bool)
+    n_band = int((~ok).sum())
+    fl_d, fl_o = dev["flags"].astype(np.uint64), ora["flags"].astype(np.uint64)
+    bits = fo.FLAG_VALID | fo.FLAG_FEASIBLE | fo.FLAG_STORED | fo.FLAG_IN_LIST | fo.FLAG_COSTED | fo.FLAG_CANDIDATE
+    for r in range(1, 11):
+        bits |= fo.reason_bit(r)
+    if check_collide:
+        bits |= fo.FLAG_COLLIDE | fo.FLAG_BOUNDARY
+    diff = ((fl_d ^ fl_o) & np.uint64(bits))
+    diff[~ok] = 0
+    assert not diff.any(), f"{int((diff != 0).sum())} flag mismatches, first rows {np.nonzero(diff)[0][:5]}, " \
+                           f"bits {[hex(int(x)) for x in diff[np.nonzero(diff)[0][:5]]]}"
+    stored = ((fl_o & np.uint64(fo.FLAG_STORED)) != 0) & ok
+    costed = ((fl_o & np.uint64(fo.FLAG_COSTED)) != 0) & ok
+    errs = {}
+    if dev["states"] is not None:
+        for f, name in enumerate(fo.FIELDS):
+            errs[name] = rel_err(dev["states"][f][stored], ora["states"][f][stored])
+    errs["costs"] = rel_err(dev["costs"][costed], ora["costs"][costed])
+    errs["total"] = rel_err(dev["total"][costed], ora["total"][costed])
+    worst = max(errs.values()) if errs else 0.0
+    assert worst < tol, f"relative error {worst:.3e} over tolerance: {errs}"
+    assert np.array_equal(dev["traj_len"][stored], ora["traj_len"][stored])
+    # selected index: exact, unless one of the two winners is itself an in-band candidate
+    wd, wo = dev["argmin"], ora["argmin"]
+    if wd != wo:
+        assert (wd >= 0 and not ok[wd]) or (wo >= 0 and not ok[wo]), (wd, wo)
+    elif wo >= 0:
+        assert abs(dev["min_cost"] - ora["min_cost"]) <= tol * max(1.0, abs(ora["min_cost"]))
+    assert abs(dev["n_in_list"] - ora["n_in_list"]) <= n_band
+    assert abs(dev["n_feasible"] - ora["n_feasible"]) <= n_band
+    assert np.all(np.abs(dev["reason_counts"].astype(float) - ora["reason_counts"]) <= n_band)
+    if check_collide and n_band == 0:
+        assert dev["collision_counter"] == ora["collision_counter"]
+    errs["in_band"] = n_band
+    return errs
