@@ -1,0 +1,417 @@
+#!/usr/bin/env python
+"""bench.py -- candidate trajectories evaluated per second per planning step (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload config2|config3|config5] [--impl reference]
+
+One "step" = one pass of the hot path (sample -> back-project -> gates -> costs -> collision ->
+arg-min) over one batch of synthetic candidates.  Default workload = BASELINE.json configs[1]
+("config2": straight reference path, 50,000-candidate (t x d x v) grid, 30 steps, 0 obstacles, fp64).
+With N > 1 (launched under torchrun) every rank evaluates its own 50,000-row shard of an N-times
+denser grid (weak scaling) and the ranks exchange the 16-byte (min_cost, row) record per step.
+
+Prints ONE JSON line (rank 0).  See DESIGN.md section 6 for how each number is obtained.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from frenetix_motion_planner_b200 import synthetic as syn  # noqa: E402
+from frenetix_motion_planner_b200.coordinate_system import CoordinateSystem  # noqa: E402
+
+METRIC = "candidate trajectories evaluated/sec per planning step"
+UNIT = "candidates/s"
+
+
+# ----------------------------------------------------------------------------------------------
+# workloads
+# ----------------------------------------------------------------------------------------------
+def build_workload(name: str, world: int):
+    """-> dict(polyline, x_cl, t1, v1, d1, N, dt, x0_orientation, v_des, low_vel, preds, rows_per_rank, label)"""
+    if name == "config2":
+        poly = syn.straight_polyline(400)
+        x_cl = ([10.0, 8.0, 0.0], [0.2, 0.0, 0.0])
+        t1 = np.round(np.arange(11, 31) * 0.1, 2)
+        v_lo, v_hi = syn.velocity_interval(8.0, syn.VEHICLE_2["a_max"], 3.0, syn.VEHICLE_2["v_max"])
+        v1 = np.linspace(v_lo, v_hi, 50 * world)            # weak scaling: denser v axis, 50k rows per rank
+        d1 = np.linspace(-3.0, 3.0, 50)
+        return dict(polyline=poly, x_cl=x_cl, t1=t1, v1=v1, d1=d1, N=30, dt=0.1, x0_orientation=0.0, v_des=8.0,
+                    v0=8.0, preds=[], rows_per_rank=50_000, scaling="weak",
+                    label="configs[1]: straight ref path (M=400), 20t x 50v x 50d = 50,000 candidates per GPU, "
+                          "31 samples, 5 cost terms, 0 obstacles, fp64")
+    if name == "config3":
+        poly = syn.arc_polyline(R=80.0, M=400)
+        x_cl = ([12.0, 9.5, 0.4], [-0.3, 0.2, -0.1])
+        t1 = np.round(np.arange(11, 31) * 0.1, 2)
+        v_lo, v_hi = syn.velocity_interval(9.5, syn.VEHICLE_2["a_max"], 3.0, syn.VEHICLE_2["v_max"])
+        v1 = np.linspace(v_lo, v_hi, 100 * world)
+        d1 = np.linspace(-3.0, 3.0, 100)
+        preds = syn.synthetic_predictions(poly, 20, 31, 0.1, seed=1234)
+        return dict(polyline=poly, x_cl=x_cl, t1=t1, v1=v1, d1=d1, N=30, dt=0.1, x0_orientation=0.2, v_des=10.0,
+                    v0=9.5, preds=preds, rows_per_rank=200_000, scaling="weak",
+                    label="configs[2]-shaped: curved ref path, 20t x 100v x 100d = 200,000 candidates per GPU, "
+                          "31 samples, 5 cost terms, 20 predicted obstacles (synthetic), fp64")
+    if name == "config5":
+        poly = syn.arc_polyline(R=200.0, M=600)
+        x_cl = ([15.0, 12.0, 0.2], [0.1, 0.05, 0.0])
+        t1 = np.unique(np.round(np.linspace(1.1, 5.0, 50), 2))
+        v_lo, v_hi = syn.velocity_interval(12.0, syn.VEHICLE_2["a_max"], 5.0, syn.VEHICLE_2["v_max"])
+        v1 = np.linspace(v_lo, v_hi, 448)
+        d1 = np.linspace(-3.0, 3.0, 447)
+        preds = syn.synthetic_predictions(poly, 50, 51, 0.1, seed=2025, s_hi=200.0)
+        total = t1.size * v1.size * d1.size
+        return dict(polyline=poly, x_cl=x_cl, t1=t1, v1=v1, d1=d1, N=50, dt=0.1, x0_orientation=0.1, v_des=13.0,
+                    v0=12.0, preds=preds, rows_per_rank=-(-total // world), scaling="strong",
+                    label=f"configs[4]: R=200 m arc, {t1.size}t x 448v x 447d = {total:,} candidates sharded over the "
+                          f"GPUs, 51 samples, 5 cost terms, 50 predicted obstacles, rows generated on device, fp64")
+    raise SystemExit(f"unknown workload {name}")
+
+
+def oracle_inputs(w):
+    from oracle import frenet_oracle as fo
+    cs = CoordinateSystem(w["polyline"])
+    ref = fo.RefPath(cs.ref_pos, cs.ref_theta, cs.ref_curv, cs.ref_curv_d,
+                     np.ascontiguousarray(w["polyline"][:, 0]), np.ascontiguousarray(w["polyline"][:, 1]))
+    prm = fo.Params(dt=w["dt"], N=w["N"], low_vel_mode=w["v0"] < 2.0, x0_orientation=w["x0_orientation"],
+                    desired_velocity=w["v_des"], draw_traj_set=True, kinematic_debug=True,
+                    cost_weights=dict(syn.DEFAULT_COST_WEIGHTS),
+                    **{k: syn.VEHICLE_2[k] for k in ("a_max", "v_switch", "delta_max", "wheelbase", "wb_rear_axle",
+                                                      "length", "width")})
+    return ref, prm
+
+
+def algorithmic_bytes_per_candidate(Nt: int, K: int, matrix_input: bool) -> int:
+    """104 B sampling row (0 when rows are generated on device) + 14 fields x Nt x 8
+    + 8 (total) + 8K (unweighted costs) + 4 (flags) + 4 (traj_len)."""
+    return (104 if matrix_input else 0) + 112 * Nt + 8 * K + 16
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.samples = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [l for (t, l) in self.samples if t0 <= t <= t1] or [l for (_, l) in self.samples[-3:]]
+        sm, mx, reasons = [], [], set()
+        for l in rows:
+            p = [x.strip() for x in l.split(",")]
+            try:
+                sm.append(float(p[0])); mx.append(float(p[1]))
+            except Exception:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU arms
+# ----------------------------------------------------------------------------------------------
+def cpu_port_throughput(w, S, budget_s=12.0, min_reps=2):
+    """Time the C/OpenMP oracle (reference-equivalent CPU path, lazy collision walk like
+    planner.py:329-392) on `S`; returns (cand/s, threads, reps, seconds)."""
+    from oracle import c_oracle
+    ref, prm = oracle_inputs(w)
+    threads = c_oracle.max_threads()
+    Tv = np.unique(S[:, 1])
+    c_oracle.plan(S[:2048], ref, prm, w["preds"], check_all_collisions=False, want_states=True, want_margins=False,
+                  T_values=Tv)                                       # warm-up
+    reps, t_acc = 0, 0.0
+    while reps < min_reps or (t_acc < budget_s and reps < 200):
+        t0 = time.perf_counter()
+        out = c_oracle.plan(S, ref, prm, w["preds"], check_all_collisions=False, want_states=True,
+                            want_margins=False, T_values=Tv)
+        t_acc += time.perf_counter() - t0
+        reps += 1
+    return S.shape[0] * reps / t_acc, threads, reps, t_acc, out
+
+
+def python_path_throughput(w, S, n=96):
+    """The restated Python path itself (numpy oracle, 1 core) on a small sample."""
+    from oracle import frenet_oracle as fo
+    ref, prm = oracle_inputs(w)
+    idx = np.linspace(0, S.shape[0] - 1, n).astype(int)
+    t0 = time.perf_counter()
+    fo.plan(S[idx], ref, prm, w["preds"], check_all_collisions=False)
+    return n / (time.perf_counter() - t0)
+
+
+def run_reference_arm(args, w, S):
+    """--impl reference: the reference's CPU path on the host cores.  The reference itself (pure
+    Python + un-vendored frenetix/commonroad wheels) cannot be installed offline, so this times the
+    C/OpenMP port in oracle/ (DESIGN.md section 6)."""
+    vals = []
+    for i in range(args.warmup + args.steps):
+        thr, threads, reps, secs, _ = cpu_port_throughput(w, S, budget_s=0.0, min_reps=1)
+        if i >= args.warmup:
+            vals.append((S.shape[0] / thr))
+    sec_per_step = float(np.mean(vals))
+    value = S.shape[0] / sec_per_step
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec_per_step * 1e3, "higher_is_better": True, "scaling": w["scaling"],
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": w["label"], "rows_per_step": int(S.shape[0]), "note": "CPU, all host threads"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"full {S.shape[0]}-row step, C/OpenMP port of the reference Python path "
+                                   f"(oracle/c/frx_oracle.c); frenetix 0.4.0 / the Python reference are not installable offline"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------
+# main
+# ----------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="config2")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+
+    w = build_workload(args.workload, world)
+    grid_mode = args.workload == "config5"
+    n_total = w["t1"].size * w["v1"].size * w["d1"].size
+    from frenetix_motion_planner_b200.dist import shard_rows
+    first, count = shard_rows(n_total, world, rank)
+
+    if args.impl == "reference":
+        if rank == 0:
+            n1 = min(n_total, w["rows_per_rank"], 200_000)
+            S = syn.grid_sampling_matrix(w["t1"], w["v1"], w["d1"], w["x_cl"])[:n1] if not grid_mode else \
+                syn.grid_sampling_matrix(w["t1"][:2], w["v1"], w["d1"], w["x_cl"])[:200_000]
+            run_reference_arm(args, w, S)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from frenetix_motion_planner_b200 import _capi, hotpath
+    from frenetix_motion_planner_b200.dist import ArgminExchange
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    # ---- set-up (not timed: once per scenario / planning cycle in the reference, too)
+    cs = CoordinateSystem(w["polyline"])
+    names, weights = hotpath.active_costs(syn.DEFAULT_COST_WEIGHTS)
+    K, Nt = len(names), w["N"] + 1
+    h = _capi.Handler(local_rank)
+    stream = torch.cuda.Stream(device=dev)
+    h.set_stream(stream.cuda_stream)
+    veh = syn.VEHICLE_2
+    h.set_params(dt=w["dt"], N=w["N"], low_vel_mode=w["v0"] < 2.0, draw_traj_set=True, kinematic_debug=True,
+                 a_max=veh["a_max"], v_switch=veh["v_switch"], delta_max=veh["delta_max"], wheelbase=veh["wheelbase"],
+                 wb_rear_axle=veh["wb_rear_axle"], length=veh["length"], width=veh["width"],
+                 x0_orientation=w["x0_orientation"], desired_velocity=w["v_des"], cost_names=names,
+                 cost_weights=weights, store_states=True, check_collisions=True)
+    h.set_reference(cs.ref_pos, cs.ref_theta, cs.ref_curv, cs.ref_curv_d, w["polyline"][:, 0], w["polyline"][:, 1])
+    h.set_time_tables(*hotpath.time_tables(np.unique(w["t1"]), w["dt"], Nt))
+    packed = hotpath.pack_predictions(w["preds"])
+    if packed is not None:
+        h.set_predictions(*packed)
+    ex = ArgminExchange() if world > 1 else None
+
+    if grid_mode:
+        S_host = None
+    else:
+        S_full = syn.grid_sampling_matrix(w["t1"], w["v1"], w["d1"], w["x_cl"])
+        S_host_t = torch.from_numpy(S_full[first:first + count].copy()).pin_memory()   # pinned host rows of this rank
+        S_host = S_host_t.numpy()
+        S_dev = S_host_t.to(dev)
+    l2_flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    launches = {"n": 0}
+    n_aux = 1 + (1 if (packed is not None) else 0)      # argmin (+ collision counter) kernels per step
+
+    def step_resident():
+        if grid_mode:
+            r = h.plan_grid(w["t1"], w["v1"], w["d1"], w["x_cl"], row_first=first, row_count=count)
+        else:
+            r = h.plan_device(S_dev.data_ptr(), count, row_index_base=first)
+        launches["n"] += 1 + n_aux
+        if ex is not None:
+            ex.exchange(r.min_cost, r.argmin, handler=h)
+        return r
+
+    def step_e2e():
+        if grid_mode:
+            r = h.plan_grid(w["t1"], w["v1"], w["d1"], w["x_cl"], row_first=first, row_count=count)
+        else:
+            r = h.plan(S_host, row_index_base=first)
+        cost, row, owner = (r.min_cost, r.argmin, 0) if ex is None else ex.exchange(r.min_cost, r.argmin, handler=h)
+        win = None
+        if row >= 0 and owner == rank:
+            win = h.get_states(np.array([row - first], dtype=np.int64))     # D2H of the selected trajectory
+        return r, row, win
+
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            l2_flush.zero_()
+            step_resident()
+        stream.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+        # ---- timed region 1: device-resident inputs, CUDA events per step on the kernel's stream
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+            time.sleep(0.25)
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        kern_ms = []
+        launches["n"] = 0
+        t_wall0 = time.perf_counter()
+        for i in range(args.steps):
+            l2_flush.zero_()                      # flush L2 (256 MiB > 126 MB) between timed iterations
+            ev[i][0].record(stream)
+            r = step_resident()
+            ev[i][1].record(stream)
+            kern_ms.append(r.eval_kernel_ms)
+        stream.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t_wall1 = time.perf_counter()
+        step_ms = [a.elapsed_time(b) for a, b in ev]
+        total_ms = float(np.sum(step_ms))
+        gpu_launches = launches["n"]
+
+        # ---- timed region 2: end to end through the C ABI with HOST buffers (wall clock)
+        for _ in range(3):
+            step_e2e()
+        stream.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            r_e2e, row_e2e, win = step_e2e()
+        stream.synchronize()
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        if world > 1:
+            dist.barrier()
+        clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+
+    # ---- max over ranks
+    if world > 1:
+        t = torch.tensor([total_ms, e2e_s, float(np.mean(kern_ms))], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, e2e_s, kern_mean_ms = t.tolist()
+        cnt = torch.tensor([count], dtype=torch.float64, device=dev)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        rows_all = int(cnt.item())
+    else:
+        kern_mean_ms = float(np.mean(kern_ms))
+        rows_all = count
+
+    if rank == 0:
+        ms_per_step = total_ms / args.steps
+        value = rows_all / (ms_per_step * 1e-3)
+        e2e_value = rows_all * args.steps / e2e_s
+        B_cand = algorithmic_bytes_per_candidate(Nt, K, matrix_input=not grid_mode)
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        achieved = count * B_cand / (kern_mean_ms * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", f"traffic_{args.workload}.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": w["scaling"], "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": w["label"], "rows_per_gpu": int(count), "rows_total": int(rows_all),
+                       "Nt": Nt, "cost_terms": names, "obstacles": len(w["preds"]),
+                       "input": "rows generated on device" if grid_mode else "sampling matrix [N,13] resident in HBM",
+                       "l2": "256 MiB L2 flush between timed iterations; per-step state output "
+                             f"{count * 112 * Nt / 1e6:.0f} MB > 126 MB L2",
+                       "timing": "sum of per-step CUDA-event intervals on the launch stream, max over ranks",
+                       "parallelism": f"{world} x B200, contiguous row shards, one 16-B all-gather per step" if world > 1 else "1 x B200"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "kernel": "frx_eval_kernel", "kernel_ms": kern_mean_ms,
+                         "algorithmic_bytes_per_candidate": B_cand, "peak_source": peak_src},
+            "e2e": {"value": e2e_value, "unit": UNIT,
+                    "h2d_bytes_per_step": int(0 if grid_mode else count * 13 * 8),
+                    "d2h_bytes_per_step": int(16 + 8 * 17 + 14 * 32 * 8),
+                    "note": "frx_plan on pinned host rows (H2D inside) + result record + selected trajectory D2H, wall clock"},
+            "gpu_launches": gpu_launches, "clocks": clocks,
+            "selected": {"row": int(row_e2e), "n_feasible": int(r_e2e.n_feasible), "n_collide": int(r_e2e.n_collide)},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            S_cpu = S_host if not grid_mode else syn.grid_sampling_matrix(w["t1"][:2], w["v1"], w["d1"], w["x_cl"])[:200_000]
+            thr, threads, reps, secs, out_cpu = cpu_port_throughput(w, S_cpu)
+            py = python_path_throughput(w, S_cpu)
+            line["cpu_baseline"] = {
+                "value": thr, "unit": UNIT, "cores": threads, "kind": "port",
+                "sample": f"{reps} x the same {S_cpu.shape[0]}-row step ({secs:.1f} s), C/OpenMP port of the reference's "
+                          f"Python path (oracle/c/frx_oracle.c)",
+                "python_path_1core": py,
+                "selected_row_matches_gpu": (bool(out_cpu["argmin"] + (0 if grid_mode else first) == row_e2e)
+                                              if not grid_mode else None)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -65,7 +65,8 @@ class FrxResult(C.Structure):
 EXPORTS = ("frx_abi_version", "frx_create", "frx_destroy", "frx_last_error", "frx_set_reference", "frx_set_params",
            "frx_set_time_tables", "frx_set_predictions", "frx_set_obstacle_positions", "frx_set_static_obbs",
            "frx_plan", "frx_plan_device", "frx_plan_grid", "frx_state_pitch", "frx_get_states",
-           "frx_get_states_range", "frx_get_costs", "frx_get_flags", "frx_device_pointers", "frx_set_stream",
+           "frx_get_states_range", "frx_get_costs", "frx_get_flags", "frx_device_pointers", "frx_winner_device_pointer",
+           "frx_set_stream",
            "frx_synchronize")
 
 _lib = None
@@ -107,6 +108,7 @@ def load_library(path: Optional[str] = None):
     lib.frx_get_costs.argtypes = [vp, C.c_int64, C.c_int64, dp, dp]
     lib.frx_get_flags.argtypes = [vp, C.c_int64, C.c_int64, C.POINTER(C.c_uint32), ip]
     lib.frx_device_pointers.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    lib.frx_winner_device_pointer.argtypes = [vp, C.POINTER(vp)]
     lib.frx_set_stream.argtypes = [vp, vp]
     lib.frx_synchronize.argtypes = [vp]
     for name in EXPORTS:
@@ -309,6 +311,11 @@ class Handler:
         ptrs = [C.c_void_p() for _ in range(4)]
         self._check(self._lib.frx_device_pointers(self._ctx, *[C.byref(p) for p in ptrs]))
         return tuple(p.value for p in ptrs)
+
+    def winner_device_pointer(self) -> int:
+        p = C.c_void_p()
+        self._check(self._lib.frx_winner_device_pointer(self._ctx, C.byref(p)))
+        return p.value
 
     def synchronize(self):
         self._check(self._lib.frx_synchronize(self._ctx))

@@ -18,9 +18,9 @@ cudaError_t frx_eval_occupancy(int Mpad, int nchunk, int* blocks_per_sm);
 void frx_launch_obstacle_prep(int O, int T, int Tp, const double* pos, const double* cov, const double* theta,
                               const double* hl, const double* hw, double* obs, cudaStream_t st);
 void frx_launch_static_prep(int B, const double* obb, double* out, cudaStream_t st);
-void frx_launch_argmin(const FrxBest* bb, int nblocks, FrxBest* out, cudaStream_t st);
-void frx_launch_collision_counter(long long N, const double* total, const uint32_t* flags, const FrxBest* winner,
-                                  unsigned long long* counters, int grid, cudaStream_t st);
+void frx_launch_argmin(const FrxBest* bb, int nblocks, long long row_base, FrxBest* out, cudaStream_t st);
+void frx_launch_collision_counter(long long N, long long row_base, const double* total, const uint32_t* flags,
+                                  const FrxBest* winner, unsigned long long* counters, int grid, cudaStream_t st);
 void frx_launch_gather(const double* states, long long N, int Ntp, const long long* idx, long long n_idx,
                        uint32_t mask, double* out, cudaStream_t st);
 
@@ -320,12 +320,12 @@ static int run_plan(frx_ctx* ctx, long long N, const double* d_sampling, bool gr
     CK(cudaEventRecord(ctx->evk0, st));
     CK(frx_launch_eval(a, nchunk, grid, st));
     CK(cudaEventRecord(ctx->evk1, st));
-    frx_launch_argmin(ctx->blockbest.p, grid, ctx->winner.p, st);
+    frx_launch_argmin(ctx->blockbest.p, grid, row_base, ctx->winner.p, st);
     CK(cudaGetLastError());
     if (p.check_collisions && (ctx->O > 0 || ctx->B > 0)) {
         long long cg = (N + 255) / 256;
         if (cg > (long long)ctx->sm_count * 4) cg = (long long)ctx->sm_count * 4;
-        frx_launch_collision_counter(N, ctx->total.p, ctx->flags.p, ctx->winner.p, ctx->counters.p, (int)cg, st);
+        frx_launch_collision_counter(N, row_base, ctx->total.p, ctx->flags.p, ctx->winner.p, ctx->counters.p, (int)cg, st);
         CK(cudaGetLastError());
     }
     CK(cudaMemcpyAsync(&ctx->h_res->winner, ctx->winner.p, sizeof(FrxBest), cudaMemcpyDeviceToHost, st));
@@ -340,7 +340,7 @@ static int run_plan(frx_ctx* ctx, long long N, const double* d_sampling, bool gr
         ctx->err = "frx_plan: a sampling row uses a duration (column 1) that is missing from frx_set_time_tables";
         return FRX_ERR_INVALID;
     }
-    out->argmin = (h.winner.idx >= 0) ? (h.winner.idx + row_base) : -1;
+    out->argmin = h.winner.idx;
     out->min_cost = (h.winner.idx >= 0) ? h.winner.cost : INFINITY;
     out->n_in_list = (int64_t)h.counters[CNT_IN_LIST];
     out->n_feasible = (int64_t)h.counters[CNT_FEASIBLE];
@@ -446,6 +446,12 @@ int frx_get_flags(frx_ctx* ctx, int64_t first, int64_t count, uint32_t* flags, i
     if (flags) CK(cudaMemcpyAsync(flags, ctx->flags.p + first, sizeof(uint32_t) * count, cudaMemcpyDeviceToHost, ctx->stream));
     if (traj_len) CK(cudaMemcpyAsync(traj_len, ctx->traj_len.p + first, sizeof(int32_t) * count, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    return FRX_OK;
+}
+
+int frx_winner_device_pointer(frx_ctx* ctx, void** winner) {
+    if (!ctx || !winner) return FRX_ERR_INVALID;
+    *winner = ctx->winner.p;
     return FRX_OK;
 }
 

@@ -160,6 +160,9 @@ int frx_get_costs(frx_ctx* ctx, int64_t first, int64_t count, double* costs, dou
 int frx_get_flags(frx_ctx* ctx, int64_t first, int64_t count, uint32_t* flags, int32_t* traj_len);
 /* raw device pointers of the last plan (states, costs, total, flags) for zero-copy consumers */
 int frx_device_pointers(frx_ctx* ctx, void** states, void** costs, void** total, void** flags);
+/* device address of the 16-byte winner record {double min_cost; int64 global_row} of the last plan:
+ * the payload of the multi-GPU arg-min exchange (all-gather of 16 B per rank, no host round trip) */
+int frx_winner_device_pointer(frx_ctx* ctx, void** winner);
 /* use an externally created stream (e.g. torch's current stream); 0 restores the private stream */
 int frx_set_stream(frx_ctx* ctx, void* cuda_stream);
 int frx_synchronize(frx_ctx* ctx);
