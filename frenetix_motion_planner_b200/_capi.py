@@ -66,7 +66,7 @@ EXPORTS = ("frx_abi_version", "frx_create", "frx_destroy", "frx_last_error", "fr
            "frx_set_time_tables", "frx_set_predictions", "frx_set_obstacle_positions", "frx_set_static_obbs",
            "frx_plan", "frx_plan_device", "frx_plan_grid", "frx_state_pitch", "frx_get_states",
            "frx_get_states_range", "frx_get_costs", "frx_get_flags", "frx_device_pointers", "frx_winner_device_pointer",
-           "frx_set_stream",
+           "frx_selftest_fdiv", "frx_set_stream",
            "frx_synchronize")
 
 _lib = None
@@ -81,7 +81,7 @@ def load_library(path: Optional[str] = None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or LIB_PATH
+    p = path or os.environ.get("FRX_LIB") or LIB_PATH     # FRX_LIB: tuning builds of the same ABI
     if not os.path.exists(p):
         raise FrxError(f"{p} not found: build the CUDA extension first (python -c 'import __graft_entry__ as g; "
                        f"g.build()'); there is no CPU fallback")
@@ -109,6 +109,7 @@ def load_library(path: Optional[str] = None):
     lib.frx_get_flags.argtypes = [vp, C.c_int64, C.c_int64, C.POINTER(C.c_uint32), ip]
     lib.frx_device_pointers.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     lib.frx_winner_device_pointer.argtypes = [vp, C.POINTER(vp)]
+    lib.frx_selftest_fdiv.argtypes = [vp, C.c_int64, dp, dp, dp, dp]
     lib.frx_set_stream.argtypes = [vp, vp]
     lib.frx_synchronize.argtypes = [vp]
     for name in EXPORTS:
@@ -311,6 +312,12 @@ class Handler:
         ptrs = [C.c_void_p() for _ in range(4)]
         self._check(self._lib.frx_device_pointers(self._ctx, *[C.byref(p) for p in ptrs]))
         return tuple(p.value for p in ptrs)
+
+    def selftest_fdiv(self, a, b):
+        a, b = _f64(a), _f64(b)
+        q1, q2 = np.empty_like(a), np.empty_like(a)
+        self._check(self._lib.frx_selftest_fdiv(self._ctx, a.size, _dptr(a), _dptr(b), _dptr(q1), _dptr(q2)))
+        return q1, q2
 
     def winner_device_pointer(self) -> int:
         p = C.c_void_p()

@@ -24,6 +24,8 @@ void frx_launch_collision_counter(long long N, long long row_base, const double*
 void frx_launch_gather(const double* states, long long N, int Ntp, const long long* idx, long long n_idx,
                        uint32_t mask, double* out, cudaStream_t st);
 
+void frx_launch_selftest_fdiv(long long n, const double* a, const double* b, double* q1, double* q2, cudaStream_t st);
+
 namespace {
 
 struct HostResult {
@@ -446,6 +448,23 @@ int frx_get_flags(frx_ctx* ctx, int64_t first, int64_t count, uint32_t* flags, i
     if (flags) CK(cudaMemcpyAsync(flags, ctx->flags.p + first, sizeof(uint32_t) * count, cudaMemcpyDeviceToHost, ctx->stream));
     if (traj_len) CK(cudaMemcpyAsync(traj_len, ctx->traj_len.p + first, sizeof(int32_t) * count, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    return FRX_OK;
+}
+
+int frx_selftest_fdiv(frx_ctx* ctx, int64_t n, const double* a, const double* b, double* q_fdiv, double* q_ieee) {
+    if (!ctx) return FRX_ERR_INVALID;
+    REQUIRE(n >= 1 && a && b && q_fdiv && q_ieee, "frx_selftest_fdiv: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    DevBuf<double> buf;
+    CK(buf.reserve((size_t)n * 4));
+    CK(cudaMemcpyAsync(buf.p, a, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(buf.p + n, b, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+    frx_launch_selftest_fdiv(n, buf.p, buf.p + n, buf.p + 2 * n, buf.p + 3 * n, ctx->stream);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(q_fdiv, buf.p + 2 * n, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(q_ieee, buf.p + 3 * n, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    buf.release();
     return FRX_OK;
 }
 

@@ -5,7 +5,13 @@
 
 #define FRX_WARPS_PER_CTA 4
 #define FRX_THREADS (FRX_WARPS_PER_CTA * 32)
+#ifndef FRX_MIN_CTAS
+#define FRX_MIN_CTAS 4   // resident CTAs per SM the eval kernel is compiled for (register cap 128)
+#endif
 #define FRX_MAX_T_VALUES 128
+#ifndef FRX_CHUNK_ROWS
+#define FRX_CHUNK_ROWS 8
+#endif
 #define FRX_EPS 1e-5
 
 // obstacle table, SoA with step pitch Tp: arr[(o * FRX_OBS_NARR + k) * Tp + t]
@@ -21,6 +27,7 @@ enum {
     CNT_REASON1,  // .. CNT_REASON1 + 9 = reason 10
     CNT_COLLISION_COUNTER = CNT_REASON1 + 10,
     CNT_T_NOT_FOUND,
+    CNT_WORK,          // chunk ticket counter of the eval kernel's dynamic scheduler
     FRX_NUM_COUNTERS
 };
 

@@ -163,6 +163,8 @@ int frx_device_pointers(frx_ctx* ctx, void** states, void** costs, void** total,
 /* device address of the 16-byte winner record {double min_cost; int64 global_row} of the last plan:
  * the payload of the multi-GPU arg-min exchange (all-gather of 16 B per rank, no host round trip) */
 int frx_winner_device_pointer(frx_ctx* ctx, void** winner);
+/* diagnostics: the kernels' slow-path-free fp64 division next to IEEE division (tests only) */
+int frx_selftest_fdiv(frx_ctx* ctx, int64_t n, const double* a, const double* b, double* q_fdiv, double* q_ieee);
 /* use an externally created stream (e.g. torch's current stream); 0 restores the private stream */
 int frx_set_stream(frx_ctx* ctx, void* cuda_stream);
 int frx_synchronize(frx_ctx* ctx);

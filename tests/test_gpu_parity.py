@@ -32,3 +32,26 @@ def test_device_matches_reference_golden_directly(name):
     assert rel_err(dev["total"][costed], g["total"][costed]) < 1e-6
     assert rel_err(dev["costs"][costed], g["costs"][costed]) < 1e-6
     assert dev["argmin"] == int(g["optimal_id"]) or not ok[dev["argmin"]] or not ok[int(g["optimal_id"])]
+
+
+def test_fdiv_is_ieee_division():
+    """The kernels' slow-path-free division (ddivg = range-checked divisor + ddivf) must equal IEEE division
+    bit for bit on its documented domain: ANY divisor, dividend 0 or within 2^+-500 (sign of a zero
+    quotient excepted)."""
+    from frenetix_motion_planner_b200 import _capi
+    h = _capi.Handler(0)
+    rng = np.random.default_rng(99)
+    n = 2_000_000
+    a = rng.normal(0, 1, n) * 10.0 ** rng.integers(-12, 12, n)
+    b = rng.normal(0, 1, n) * 10.0 ** rng.integers(-12, 12, n)
+    a[:1000] = 0.0; a[1000:2000] = -0.0
+    b[2100:2200] = np.array([1e-310, 1e300, np.inf, 0.0, np.nan] * 20)     # degenerate divisors -> fallback
+    b[2200:2300] = 0.1; a[2200:2300] = np.linspace(-3, 3, 100)
+    b[2300:2400] = 100000.0; a[2300:2400] = np.rint(rng.normal(0, 1e5, 100))
+    q1, q2 = h.selftest_fdiv(a, b)
+    same = (q1 == q2) | (np.isnan(q1) & np.isnan(q2))
+    assert same.all(), f"{(~same).sum()} mismatches, e.g. {a[~same][:3]} / {b[~same][:3]}"
+    with np.errstate(all="ignore"):
+        ref = a / b
+    same_host = (q1 == ref) | (np.isnan(q1) & np.isnan(ref))
+    assert same_host.all()
