@@ -1,0 +1,460 @@
+"""``ReactivePlannerB200`` -- drop-in for ``ReactivePlannerPython`` / ``ReactivePlannerCpp`` whose inner loop
+(sample -> back-project -> kinematic gates -> costs -> collision -> arg-min) runs on a B200 through
+libfrx_b200.so.
+
+Plug-in point in the reference: ``FrenetPlannerInterface.__init__`` picks the planner class
+(cr_scenario_handler/planner_interfaces/frenet_interface.py:71-73); INTEGRATION.md shows the two-line
+patch.  Same 7-argument constructor and the same public surface as
+frenetix_motion_planner/reactive_planner.py:36-130 and the ``Planner`` base (planner.py:45-710):
+``plan()``, ``update_externals()``, ``set_reference_and_coordinate_system()``, ``set_cost_function()``,
+``set_predictions()``, ``set_x_0/set_x_cl/set_desired_velocity``, attributes ``all_traj``,
+``optimal_trajectory``, ``trajectory_pair``, ``infeasible_count_collision``,
+``_infeasible_count_kinematics``, ``infeasible_kinematics_percentage``, ``x_0``, ``x_cl``,
+``coordinate_system``, ``record_state_list``, ``record_input_list``, ``ego_vehicle_history``.
+
+Host-side work per plan() is what the reference also does on the host once per step (level sets,
+sampling matrix, bookkeeping); nothing per-candidate happens in Python.  The CommonRoad object
+conversions of the reference (``Trajectory`` / ``DynamicObstacle``) need commonroad-io; when it is not
+importable, light-weight containers with the same attribute names are returned instead.
+"""
+from __future__ import annotations
+
+import logging
+import math
+import time
+from types import SimpleNamespace
+from typing import List, Optional, Tuple
+
+import numpy as np
+
+from . import _capi, hotpath
+from .coordinate_system import CoordinateSystem
+from .sampling_matrix import SamplingHandler, python_path_rows, sampling_axes
+from .trajectories import TrajectoryBundle, TrajectorySample, CartesianSample, CurviLinearSample
+
+_EPS = 1e-5
+
+
+def _get(obj, name, default=None):
+    """Attribute-or-key access (OmegaConf objects, plain namespaces and dicts all work)."""
+    if obj is None:
+        return default
+    if isinstance(obj, dict):
+        return obj.get(name, default)
+    return getattr(obj, name, default)
+
+
+class PlannerState(SimpleNamespace):
+    """Minimal stand-in for ReactivePlannerState (state.py:14-39): rear-axle position, orientation,
+    velocity, acceleration, yaw_rate, steering_angle, time_step."""
+
+    def shift_positions_to_center(self, wb_rear_axle: float):
+        c = PlannerState(**self.__dict__)
+        c.position = np.asarray(self.position, dtype=float) + wb_rear_axle * np.array(
+            [np.cos(self.orientation), np.sin(self.orientation)])
+        return c
+
+
+class _Trajectory(SimpleNamespace):
+    """(initial_time_step, state_list) like commonroad's Trajectory."""
+
+
+class ReactivePlannerB200:
+    def __init__(self, config_plan, config_sim, scenario=None, planning_problem=None, log_path=None, work_dir=None,
+                 msg_logger=None, device: int = 0):
+        self.config_plan, self.config_sim = config_plan, config_sim
+        planning, debug = _get(config_plan, "planning"), _get(config_plan, "debug")
+        self.horizon = _get(planning, "planning_horizon")
+        self.dT = _get(planning, "dt")
+        self.N = int(self.horizon / self.dT)
+        assert self.dT > 0 and self.N > 0 and self.horizon > 0
+        self.vehicle_params = _get(config_sim, "vehicle")
+        self._low_vel_mode_threshold = _get(planning, "low_vel_mode_threshold", 2.0)
+        self.msg_logger = msg_logger or logging.getLogger("Message_logger")
+        self._multiproc = bool(_get(debug, "multiproc", False))
+        self._num_workers = _get(debug, "num_workers", 1)
+        self.x_0 = None
+        self.x_cl: Optional[Tuple[List, List]] = None
+        self.reference_path = None
+        self.record_state_list, self.record_input_list, self.ego_vehicle_history = [], [], []
+        self._LOW_VEL_MODE = False
+        self.coordinate_system: Optional[CoordinateSystem] = None
+        self.scenario, self.road_boundary = scenario, None
+        self.planning_problem = planning_problem
+        self.predictions = None
+        self.reach_set = self.behavior = self.set_new_ref_path = None
+        self.goal_status, self.full_goal_status, self.goal_area = False, None, None
+        self.occlusion_module, self.use_occ_model = None, False
+        self.goal_message = "Planner is in time step 0!"
+        self.desired_velocity = None
+        self._desired_d = 0.
+        self.use_prediction = False
+        self._collision_counter = 0
+        self._total_count = 0
+        self._infeasible_count_kinematics = None
+        self.infeasible_kinematics_percentage = None
+        self._sampling_min = _get(planning, "sampling_min", 2)
+        self._sampling_max = _get(planning, "sampling_max", 3)
+        self.sampling_handler = SamplingHandler(dt=self.dT, max_sampling_number=self._sampling_max,
+                                                t_min=_get(planning, "t_min", 1.1), horizon=self.horizon,
+                                                delta_d_max=_get(planning, "d_max", 3), delta_d_min=_get(planning, "d_min", -3),
+                                                d_ego_pos=_get(planning, "d_ego_pos", False))
+        self.stopping_s = None
+        self.log_risk = bool(_get(debug, "log_risk", False))
+        self.save_all_traj = bool(_get(debug, "save_all_traj", False))
+        self.all_traj = None
+        self.optimal_trajectory = None
+        self.trajectory_pair = None
+        self.logger = None                      # DataLoggingCosts of the reference plugs in here when available
+        self._draw_traj_set = bool(_get(debug, "draw_traj_set", True))
+        self._kinematic_debug = bool(_get(debug, "kinematic_debug", True))
+        # "cpp" sampling adds {N*dT}, {ss0} to the level sets like reactive_planner_cpp.py:235-237
+        self.sampling_style = _get(debug, "sampling_style", "python")
+        self.static_obbs = None                 # road-boundary stand-in: [[cx, cy, theta, half_len, half_wid], ...]
+        self.obstacle_order = None              # ids in scenario.obstacles order (collision_check.py:127-131)
+        self.collision_check_enabled = True     # False: selection = first of the cost-sorted list (tests)
+
+        self.cost_weights = dict(_get(_get(config_plan, "cost"), "cost_weights", {}) or {})
+        self.set_cost_function(self.cost_weights)
+
+        # ---- device side: fails loudly if libfrx_b200.so or the GPU is missing (no CPU fallback)
+        self.handler = _capi.Handler(device)
+        self._bundle: Optional[TrajectoryBundle] = None
+        self._ref_dirty = True
+        self._pred_dirty = True
+        self.last_plan_stats = None
+
+    # ------------------------------------------------------------------------------------------
+    # setters of the Planner base class (planner.py:172-310, 671-710)
+    # ------------------------------------------------------------------------------------------
+    @property
+    def infeasible_count_collision(self):
+        return self._collision_counter
+
+    def set_cost_function(self, cost_weights):
+        """Accepts a weight dict (what the cpp planner takes, reactive_planner_cpp.py:114-141) or an object with
+        ``cost_weights`` (an AdaptableCostFunction of the reference)."""
+        w = _get(cost_weights, "cost_weights", cost_weights)
+        self.cost_weights = dict(w)
+        self.cost_names, self.cost_weight_list = hotpath.active_costs(self.cost_weights)
+        unsupported = [n for n in self.cost_names if n not in _capi.COST_ID]
+        if unsupported:
+            raise NotImplementedError(f"cost terms {unsupported} are host-only / unimplemented in the reference "
+                                      f"(partial_cost_functions.py:67-117,133-138,199-293,359-387)")
+        self.cost_function = SimpleNamespace(cost_weights=self.cost_weights, cost_weights_names=self.cost_names)
+
+    def set_predictions(self, predictions: dict):
+        self.use_prediction = True
+        self.predictions = predictions
+        self._pred_dirty = True
+
+    def set_reference_and_coordinate_system(self, reference_path: np.ndarray = None, coordinate_system=None):
+        """Reference tables for the device; an existing CoordinateSystem (e.g. the reference's CCosy wrapper)
+        can be handed in instead of a polyline."""
+        if coordinate_system is None:
+            coordinate_system = CoordinateSystem(reference=reference_path)
+        self.coordinate_system = coordinate_system
+        self.reference_path = np.asarray(coordinate_system.reference)
+        self.set_new_ref_path = True
+        self._ref_dirty = True
+
+    def set_scenario(self, scenario):
+        self.scenario = scenario
+
+    def set_static_obstacles(self, obbs):
+        self.static_obbs = None if obbs is None else np.asarray(obbs, dtype=np.float64).reshape(-1, 5)
+
+    def set_x_0(self, x_0):
+        self.x_0 = x_0
+        self._LOW_VEL_MODE = bool(x_0.velocity < self._low_vel_mode_threshold)     # planner.py:222-229
+
+    def set_x_cl(self, x_cl):
+        # planner.py:231-237: a given x_cl is only trusted once one exists and the reference path is unchanged;
+        # (extension) a caller without a Cartesian position can seed the Frenet state directly
+        if x_cl is not None and ((self.x_cl is not None and not self.set_new_ref_path)
+                                 or getattr(self.x_0, "position", None) is None):
+            self.x_cl = x_cl
+        else:
+            self.x_cl = self._compute_initial_states(self.x_0)
+        self.set_new_ref_path = False
+
+    def set_desired_velocity(self, desired_velocity: float, current_speed: float = None, stopping: bool = False,
+                             v_limit: float = 36):
+        self.desired_velocity = desired_velocity
+        a_max, v_max = _get(self.vehicle_params, "a_max"), _get(self.vehicle_params, "v_max")
+        min_v = max(0.001, current_speed - a_max * self.horizon)                    # planner.py:304-306
+        max_v = min(min(current_speed + (a_max / 6.0) * self.horizon, v_limit), v_max)
+        self.sampling_handler.set_v_sampling(min_v, max_v)
+
+    def set_goal_area(self, goal_area):
+        self.goal_area = goal_area
+
+    def set_planning_problem(self, planning_problem):
+        self.planning_problem = planning_problem
+
+    def set_occlusion_module(self, occ_module):
+        raise NotImplementedError("the occlusion module re-ranks candidates on the host (external package); "
+                                  "out of scope of the device hot path")
+
+    def set_reach_set(self, reach_set):
+        self.reach_set = reach_set
+
+    def set_behavior(self, behavior):
+        self.behavior = behavior
+
+    def set_ego_vehicle_state(self, current_ego_vehicle):
+        self.ego_vehicle_history.append(current_ego_vehicle)
+
+    def set_sampling_parameters(self, t_min: float, horizon: float, delta_d_min: float, delta_d_max: float):
+        self.sampling_handler.update_static_params(t_min, horizon, delta_d_min, delta_d_max)
+
+    def record_state_and_input(self, state):
+        self.record_state_list.append(state)
+        if len(self.record_state_list) > 1:
+            rate = (state.steering_angle - self.record_state_list[-2].steering_angle) / self.dT
+        else:
+            rate = 0.0
+        self.record_input_list.append(SimpleNamespace(time_step=state.time_step, acceleration=state.acceleration,
+                                                      steering_angle_speed=rate))
+
+    def update_externals(self, scenario=None, reference_path=None, planning_problem=None, goal_area=None, x_0=None,
+                         x_cl=None, cost_weights=None, occlusion_module=None, desired_velocity=None, predictions=None,
+                         reach_set=None, behavior=None):
+        """planner.py:172-217, same order of effects."""
+        if scenario is not None:
+            self.set_scenario(scenario)
+        if reference_path is not None:
+            self.set_reference_and_coordinate_system(reference_path)
+        if planning_problem is not None:
+            self.set_planning_problem(planning_problem)
+        if goal_area is not None:
+            self.set_goal_area(goal_area)
+        if x_0 is not None:
+            self.set_x_0(x_0)
+            self.set_x_cl(x_cl)
+        if cost_weights is not None:
+            self.set_cost_function(cost_weights)
+        if occlusion_module is not None:
+            self.set_occlusion_module(occlusion_module)
+        if desired_velocity is not None:
+            self.set_desired_velocity(desired_velocity, x_0.velocity)
+        if predictions is not None:
+            self.set_predictions(predictions)
+        if reach_set is not None:
+            self.set_reach_set(reach_set)
+        if behavior is not None:
+            self.set_behavior(behavior)
+        if self.sampling_handler.d_ego_pos:
+            self.sampling_handler.set_d_sampling(self.x_cl[1][0])
+
+    # ------------------------------------------------------------------------------------------
+    # Frenet initial state (planner.py:567-635)
+    # ------------------------------------------------------------------------------------------
+    def _compute_initial_states(self, x_0):
+        cs = self.coordinate_system
+        s, d = cs.convert_to_curvilinear_coords(x_0.position[0], x_0.position[1])
+        s_idx = int(np.argmax(cs.ref_pos > s)) - 1
+        s_lambda = (s - cs.ref_pos[s_idx]) / (cs.ref_pos[s_idx + 1] - cs.ref_pos[s_idx])
+        ref_theta = np.unwrap(cs.ref_theta)
+        theta_ref = (ref_theta[s_idx + 1] - ref_theta[s_idx]) * (s - cs.ref_pos[s_idx]) / \
+                    (cs.ref_pos[s_idx + 1] - cs.ref_pos[s_idx]) + ref_theta[s_idx]
+        theta_ref = hotpath_make_valid_orientation(theta_ref)
+        theta_cl = x_0.orientation - theta_ref
+        kr = (cs.ref_curv[s_idx + 1] - cs.ref_curv[s_idx]) * s_lambda + cs.ref_curv[s_idx]
+        kr_d = (cs.ref_curv_d[s_idx + 1] - cs.ref_curv_d[s_idx]) * s_lambda + cs.ref_curv_d[s_idx]
+        wheelbase = _get(self.vehicle_params, "wheelbase")
+        kappa_0 = np.tan(getattr(x_0, "steering_angle", 0.0)) / wheelbase
+        d_p = (1 - kr * d) * np.tan(theta_cl)
+        d_pp = -(kr_d * d + kr * d_p) * np.tan(theta_cl) + ((1 - kr * d) / (math.cos(theta_cl) ** 2)) * (
+                kappa_0 * (1 - kr * d) / math.cos(theta_cl) - kr)
+        s_velocity = x_0.velocity * math.cos(theta_cl) / (1 - kr * d)
+        if s_velocity < 0:
+            raise Exception("Initial state or reference incorrect! Curvilinear velocity is negative which indicates "
+                            "that the ego vehicle is not driving in the same direction as specified by the reference")
+        s_acceleration = getattr(x_0, "acceleration", 0.0)
+        s_acceleration -= (s_velocity ** 2 / math.cos(theta_cl)) * (
+                (1 - kr * d) * np.tan(theta_cl) * (kappa_0 * (1 - kr * d) / (math.cos(theta_cl)) - kr) -
+                (kr_d * d + kr * d_p))
+        s_acceleration /= ((1 - kr * d) / (math.cos(theta_cl)))
+        if self._LOW_VEL_MODE:
+            d_velocity, d_acceleration = d_p, d_pp
+        else:
+            d_velocity = x_0.velocity * math.sin(theta_cl)
+            d_acceleration = s_acceleration * d_p + s_velocity ** 2 * d_pp
+        return [s, s_velocity, s_acceleration], [d, d_velocity, d_acceleration]
+
+    # ------------------------------------------------------------------------------------------
+    # the hot path
+    # ------------------------------------------------------------------------------------------
+    def _push_static_inputs(self):
+        h, cs, vp = self.handler, self.coordinate_system, self.vehicle_params
+        h.set_params(dt=self.dT, N=self.N, low_vel_mode=self._LOW_VEL_MODE, draw_traj_set=self._draw_traj_set,
+                     kinematic_debug=self._kinematic_debug, a_max=_get(vp, "a_max"), v_switch=_get(vp, "v_switch"),
+                     delta_max=_get(vp, "delta_max"), wheelbase=_get(vp, "wheelbase"),
+                     wb_rear_axle=_get(vp, "wb_rear_axle"), length=_get(vp, "length"), width=_get(vp, "width"),
+                     x0_orientation=self.x_0.orientation, desired_velocity=self.desired_velocity,
+                     cost_names=self.cost_names, cost_weights=self.cost_weight_list, store_states=True,
+                     check_collisions=self.collision_check_enabled and (self.use_prediction or self.static_obbs is not None))
+        if self._ref_dirty:
+            ref = np.asarray(cs.reference)
+            h.set_reference(cs.ref_pos, cs.ref_theta, cs.ref_curv, cs.ref_curv_d, ref[:, 0], ref[:, 1])
+            self._ref_dirty = False
+        if self._pred_dirty:
+            packed = hotpath.pack_predictions(self.predictions, self.obstacle_order) if self.use_prediction else None
+            if packed is None:
+                h.set_predictions(None, None, None, [], [], [])
+            else:
+                h.set_predictions(*packed)
+            self._pred_dirty = False
+        h.set_static_obbs(self.static_obbs)
+        if "distance_to_obstacles" in self.cost_names:
+            h.set_obstacle_positions(getattr(self, "obstacle_positions", None))
+
+    def _sampling_matrix(self, samp_level: int) -> np.ndarray:
+        t_set, v_set, d_set = sampling_axes(self.sampling_handler, samp_level, self.x_cl,
+                                            cpp_style=(self.sampling_style == "cpp"))
+        return python_path_rows(t_set, v_set, d_set, self.x_cl)
+
+    def _evaluate(self, sampling: np.ndarray) -> Tuple[TrajectoryBundle, "hotpath.PlanOutput"]:
+        if self._bundle is not None:
+            self._bundle = None                  # device buffers are recycled by the next plan
+        self.handler.set_time_tables(*hotpath.time_tables(hotpath.distinct_durations(sampling), self.dT, self.N + 1))
+        res = hotpath.PlanOutput.from_result(self.handler.plan(sampling))
+        bundle = TrajectoryBundle(self.handler, sampling.shape[0], self.cost_names, self.cost_weight_list, self.dT,
+                                  self.horizon, self.N + 1, self._LOW_VEL_MODE, sampling=sampling)
+        self._bundle = bundle
+        return bundle, res
+
+    def plan(self) -> tuple:
+        """reactive_planner.py:67-130 with the per-candidate work on the device."""
+        optimal_trajectory = None
+        t0 = time.time()
+        self._push_static_inputs()
+        samp_level = self._sampling_min
+        bundle = None
+        while optimal_trajectory is None and samp_level < self._sampling_max:
+            sampling = self._sampling_matrix(samp_level)
+            self._total_count = sampling.shape[0]
+            bundle, res = self._evaluate(sampling)
+            optimal_trajectory = self._get_optimal_trajectory(bundle, res, samp_level)
+            samp_level += 1
+        planning_time = time.time() - t0
+        self.trajectory_pair = self._compute_trajectory_pair(optimal_trajectory) if optimal_trajectory is not None else None
+        if self.trajectory_pair is not None:
+            self.set_ego_vehicle_state(self.convert_state_list_to_commonroad_object(self.trajectory_pair[0].state_list))
+        if optimal_trajectory is None and self.x_0.velocity <= 0.1:
+            self.msg_logger.warning('Planning standstill for the current scenario')
+            optimal_trajectory = self._compute_standstill_trajectory()
+        self.optimal_trajectory = optimal_trajectory
+        self.plan_postprocessing(optimal_trajectory=optimal_trajectory, planning_time=planning_time)
+        return self.trajectory_pair
+
+    def _get_optimal_trajectory(self, bundle: TrajectoryBundle, res, samp_lvl):
+        """reactive_planner.py:184-272: statistics, all_traj, selection (device arg-min == first collision-free
+        entry of the cost-sorted feasible list)."""
+        self._collision_counter = res.collision_counter
+        counts = [0] * 11
+        if self._multiproc and self._kinematic_debug:          # only then do the per-reason counts travel back
+            counts = [int(v) for v in res.reason_counts]       # (reactive_planner.py:218-220)
+        counts[0] = int(res.reason_counts[0])
+        self._infeasible_count_kinematics = counts
+        self.infeasible_kinematics_percentage = float(res.n_feasible / res.n_in_list) * 100 if res.n_in_list else 0.0
+        self.last_plan_stats = res
+        if self._draw_traj_set or self.save_all_traj:
+            bundle.sort()
+            self.all_traj = bundle.trajectories
+        if res.argmin >= 0:
+            return bundle.sample(res.argmin)
+        if samp_lvl >= self._sampling_max - 1 and res.n_feasible > 0:
+            # reference: lowest ego_risk + obst_risk among the feasible ones (needs risk_assessment, host side);
+            # a user-supplied risk function keeps that behaviour, otherwise the cheapest feasible one is taken
+            fl = bundle.flags
+            feas = np.flatnonzero(((fl & _capi.FLAG_VALID) != 0) & ((fl & _capi.FLAG_FEASIBLE) != 0) &
+                                  ((fl & _capi.FLAG_IN_LIST) != 0))
+            risk_fn = getattr(self, "risk_function", None)
+            self.msg_logger.warning("No optimal trajectory available. Select lowest risk trajectory!")
+            if risk_fn is not None:
+                risks = np.array([risk_fn(bundle.sample(int(r))) for r in feas])
+                return bundle.sample(int(feas[np.argmin(risks)]))
+            return bundle.sample(int(feas[np.argmin(bundle.total[feas])]))
+        return None
+
+    # ------------------------------------------------------------------------------------------
+    # output conversion (planner.py:394-515) without commonroad-io
+    # ------------------------------------------------------------------------------------------
+    def _compute_trajectory_pair(self, trajectory: TrajectorySample) -> tuple:
+        c, cl = trajectory.cartesian, trajectory.curvilinear
+        t0 = getattr(self.x_0, "time_step", 0)
+        wheelbase = _get(self.vehicle_params, "wheelbase")
+        cart_list, cl_list, lon_list, lat_list = [], [], [], []
+        for i in range(len(c.x)):
+            yaw = (c.theta[i] - c.theta[i - 1]) / self.dT if i > 0 else getattr(self.x_0, "yaw_rate", 0.0)
+            cart_list.append(PlannerState(time_step=t0 + i, position=np.array([c.x[i], c.y[i]]), orientation=c.theta[i],
+                                          velocity=c.v[i], acceleration=c.a[i], yaw_rate=yaw,
+                                          steering_angle=np.arctan2(wheelbase * c.kappa[i], 1.0)))
+            cl_list.append(SimpleNamespace(time_step=t0 + i, position=np.array([cl.s[i], cl.d[i]]), velocity=c.v[i],
+                                           acceleration=c.a[i], orientation=c.theta[i], yaw_rate=c.kappa[i]))
+            lon_list.append([cl.s[i], cl.s_dot[i], cl.s_ddot[i]])
+            lat_list.append([cl.d[i], cl.d_dot[i], cl.d_ddot[i]])
+        cart = _Trajectory(initial_time_step=t0, state_list=cart_list)
+        lo, hi = self.x_0.orientation - np.pi, self.x_0.orientation + np.pi      # shift_orientation, planner.py:536-542
+        for st in cart.state_list:
+            while st.orientation < lo:
+                st.orientation += 2 * np.pi
+            while st.orientation > hi:
+                st.orientation -= 2 * np.pi
+        return cart, _Trajectory(initial_time_step=t0, state_list=cl_list), lon_list, lat_list
+
+    def convert_state_list_to_commonroad_object(self, state_list, obstacle_id: int = 42):
+        wb_rear = _get(self.vehicle_params, "wb_rear_axle")
+        shifted = [s.shift_positions_to_center(wb_rear) for s in state_list]
+        return SimpleNamespace(obstacle_id=obstacle_id, initial_state=shifted[0],
+                               obstacle_shape=SimpleNamespace(length=_get(self.vehicle_params, "length"),
+                                                              width=_get(self.vehicle_params, "width")),
+                               prediction=SimpleNamespace(trajectory=_Trajectory(
+                                   initial_time_step=shifted[0].time_step, state_list=shifted)))
+
+    def _compute_standstill_trajectory(self):
+        """reactive_planner.py:579-626 (host only; used when nothing is selectable and v <= 0.1)."""
+        x_0, (x_0_lon, x_0_lat) = self.x_0, self.x_cl
+        N = self.N
+        kappa_0 = np.tan(getattr(x_0, "steering_angle", 0.0)) / _get(self.vehicle_params, "wheelbase")
+        a = np.repeat(0.0, N)
+        a[1] = -x_0.velocity / self.dT
+        cart = CartesianSample(np.repeat(x_0.position[0], N), np.repeat(x_0.position[1], N),
+                               np.repeat(x_0.orientation, N), np.repeat(0.0, N), a, np.repeat(kappa_0, N),
+                               np.repeat(0.0, N), current_time_step=N)
+        cs = self.coordinate_system
+        s_idx = int(np.argmax(cs.ref_pos > x_0_lon[0])) - 1
+        ref_theta = np.unwrap(cs.ref_theta)
+        th = (ref_theta[s_idx + 1] - ref_theta[s_idx]) * (x_0_lon[0] - cs.ref_pos[s_idx]) / \
+             (cs.ref_pos[s_idx + 1] - cs.ref_pos[s_idx]) + ref_theta[s_idx]
+        theta_cl = x_0.orientation - hotpath_make_valid_orientation(th)
+        curv = CurviLinearSample(np.repeat(x_0_lon[0], N), np.repeat(x_0_lat[0], N), np.repeat(theta_cl, N), N,
+                                 dd=np.repeat(x_0_lat[1], N), ddd=np.repeat(x_0_lat[2], N),
+                                 ss=np.repeat(x_0_lon[1], N), sss=np.repeat(x_0_lon[2], N))
+        return SimpleNamespace(cartesian=cart, curvilinear=curv, uniqueId=0, cost=0.0, feasible=True, valid=True,
+                               horizon=self.horizon, dt=self.dT, costMap={n: (0, 0) for n in self.cost_names},
+                               _ego_risk=None, _obst_risk=None, boundary_harm=None, _coll_detected=None,
+                               actual_traj_length=N)
+
+    def plan_postprocessing(self, optimal_trajectory, planning_time, replanning_counter=0):
+        """planner.py:637-649: hand the result to the reference's logger when one is attached."""
+        if optimal_trajectory is not None and self.logger:
+            self.logger.log(optimal_trajectory, time_step=self.x_0.time_step,
+                            infeasible_kinematics=self._infeasible_count_kinematics,
+                            percentage_kinematics=self.infeasible_kinematics_percentage, planning_time=planning_time,
+                            ego_vehicle=self.ego_vehicle_history[-1], desired_velocity=self.desired_velocity,
+                            replanning_counter=replanning_counter)
+            self.logger.log_predicition(self.predictions)
+        if self.save_all_traj and self.logger:
+            self.logger.log_all_trajectories(self.all_traj, self.x_0.time_step)
+
+
+def hotpath_make_valid_orientation(angle: float) -> float:
+    """commonroad.common.util.make_valid_orientation (restated)."""
+    two_pi = 2.0 * np.pi
+    angle = angle % two_pi
+    if np.pi <= angle <= two_pi:
+        angle = angle - two_pi
+    return angle

@@ -1,0 +1,115 @@
+"""CPU-only tests of the host layer: level sets / sampling matrix against the reference's own outputs,
+time tables, packing, sharding, the C-ABI surface, and loud failure without a GPU."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from helpers import GOLDEN_DIR, load_golden
+from oracle import frenet_oracle as fo
+from frenetix_motion_planner_b200 import hotpath, synthetic as syn
+from frenetix_motion_planner_b200.sampling_matrix import (SamplingHandler, generate_sampling_matrix, python_path_rows,
+                                                          sampling_axes)
+from frenetix_motion_planner_b200.dist import shard_rows, reduce_winners
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_level_sets_and_matrix_match_reference_outputs():
+    g = np.load(os.path.join(GOLDEN_DIR, "ref_sampling.npz"))
+    sh = SamplingHandler(dt=0.1, max_sampling_number=3, t_min=1.1, horizon=3.0, delta_d_max=3, delta_d_min=-3,
+                         d_ego_pos=False)
+    sh.set_v_sampling(0.001, 13.75)
+    for lvl in range(3):
+        assert np.array_equal(np.array(sorted(sh.t_sampling.to_range(lvl))), g[f"t_{lvl}"])
+        assert np.array_equal(np.array(sorted(sh.v_sampling.to_range(lvl))), g[f"v_{lvl}"])
+        assert np.array_equal(np.array(sorted(sh.d_sampling.to_range(lvl))), g[f"d_{lvl}"])
+    M = generate_sampling_matrix(t0_range=0.0, t1_range=g["m_t1"], s0_range=10.0, ss0_range=8.0, sss0_range=0.5,
+                                 ss1_range=g["m_v1"], sss1_range=0, d0_range=0.2, dd0_range=0.1, ddd0_range=-0.1,
+                                 d1_range=g["m_d1"], dd1_range=0.0, ddd1_range=0.0)
+    assert np.array_equal(M, g["matrix"])
+    x_cl = ([10.0, 8.0, 0.5], [0.2, 0.1, -0.1])
+    assert np.array_equal(syn.grid_sampling_matrix(g["m_t1"], g["m_v1"], g["m_d1"], x_cl), g["matrix"])
+
+
+@pytest.mark.parametrize("name,v0", [("straight_hv_draw", 8.0), ("arc_hv_draw_pred", 9.5), ("scurve_lowvel_draw", 1.2)])
+def test_python_path_row_order_equals_reference_generation_order(name, v0):
+    """Row index == the reference's uniqueId: same sets, same iteration order (reactive_planner.py:149-175)."""
+    g, ref, prm, preds = load_golden(name)
+    x_cl = (list(g["x_cl_lon"]), list(g["x_cl_lat"]))
+    sh = SamplingHandler(dt=0.1, max_sampling_number=3, t_min=1.1, horizon=3.0, delta_d_max=3, delta_d_min=-3,
+                         d_ego_pos=False)
+    sh.set_v_sampling(*syn.velocity_interval(v0, syn.VEHICLE_2["a_max"], 3.0, syn.VEHICLE_2["v_max"]))
+    rows = python_path_rows(*sampling_axes(sh, 2, x_cl), x_cl)
+    assert np.array_equal(rows, g["sampling"])
+    t, v, d = sampling_axes(sh, 2, x_cl, cpp_style=True)
+    assert len(t) * len(v) * len(d) == 800        # the C++ path's 8 x 10 x 10
+
+
+def test_time_tables_follow_numpy_semantics():
+    for T in (1.1, 1.4, 1.7, 2.0, 2.3, 2.6, 2.9, 3.0):
+        n, tp = hotpath.time_table(T, 0.1, 31)
+        t, t2, t3, t4, t5 = fo.time_grid(T, 0.1)
+        assert n == len(t)
+        for k, a in enumerate((t, t2, t3, t4, t5)):
+            assert np.array_equal(tp[k, :n], a) and not tp[k, n:].any()
+    assert hotpath.time_table(1.1, 0.1, 31)[0] == 13        # np.arange length quirk
+    with pytest.raises(ValueError):
+        hotpath.time_table(3.2, 0.1, 31)
+
+
+def test_distinct_durations_and_packing():
+    S = syn.grid_sampling_matrix([1.1, 2.0, 3.0], [1.0, 2.0], [0.0, 0.5, 1.0], ([0, 1, 0], [0, 0, 0]))
+    assert np.array_equal(hotpath.distinct_durations(S), [1.1, 2.0, 3.0])
+    assert np.array_equal(hotpath.distinct_durations(S[np.random.default_rng(0).permutation(len(S))]), [1.1, 2.0, 3.0])
+    preds = syn.synthetic_predictions(syn.straight_polyline(200), 3, 31, 0.1, seed=1)
+    preds[1]["pos_list"] = preds[1]["pos_list"][:10]; preds[1]["cov_list"] = preds[1]["cov_list"][:10]
+    pos, cov, th, hl, hw, ln = hotpath.pack_predictions({7: preds[0], 3: preds[1], 9: preds[2]}, obstacle_order=[3, 9, 7])
+    assert list(ln) == [10, 31, 31] and pos.shape == (3, 31, 2) and np.array_equal(pos[2], preds[0]["pos_list"])
+    assert np.array_equal(cov[0, 10:], np.tile(np.eye(2), (21, 1, 1))) and hl[0] == 2.75
+    assert hotpath.pack_predictions({}) is None
+    names, w = hotpath.active_costs({"b": 1.0, "a": 0.5, "zero": 0.0})
+    assert names == ["a", "b"] and w == [0.5, 1.0]
+
+
+def test_shards_cover_rows_once_and_reduce_is_deterministic():
+    for n, ws in ((10, 3), (50_000, 8), (7, 8), (10_010_624, 8)):
+        spans = [shard_rows(n, ws, r) for r in range(ws)]
+        assert sum(c for _, c in spans) == n
+        assert all(spans[i][0] + spans[i][1] == spans[i + 1][0] or spans[i + 1][1] == 0 for i in range(ws - 1))
+    assert reduce_winners(np.array([3.0, 1.0, 1.0, np.inf]), np.array([5, 40, 12, -1])) == (1.0, 12)
+    assert reduce_winners(np.array([np.inf, np.inf]), np.array([-1, -1])) == (float("inf"), -1)
+
+
+def test_c_abi_library_exports_every_declared_symbol():
+    from frenetix_motion_planner_b200 import _capi
+    hdr = open(os.path.join(ROOT, "include", "frx.h")).read()
+    declared = set(re.findall(r"\b(frx_[a-z_0-9]+)\s*\(", hdr))
+    declared.discard("frx_ctx")
+    assert len(declared) >= 20
+    lib = _capi.load_library()
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/frx.h but not exported by libfrx_b200.so"
+    assert set(_capi.EXPORTS) == declared
+    assert lib.frx_abi_version() == 1
+
+
+def test_no_cpu_fallback_without_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from frenetix_motion_planner_b200 import _capi
+    with pytest.raises(_capi.FrxError):
+        _capi.Handler(0)
+    with pytest.raises(_capi.FrxError):
+        _capi.load_library("/nonexistent/libfrx_b200.so")
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "frenetix_motion_planner_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in txt.replace("oracle/", "").replace("the oracle", "").lower() or f == "synthetic.py", f
