@@ -75,6 +75,25 @@ def build_workload(name: str, world: int):
                     v0=12.0, preds=preds, rows_per_rank=-(-total // world), scaling="strong",
                     label=f"configs[4]: R=200 m arc, {t1.size}t x 448v x 447d = {total:,} candidates sharded over the "
                           f"GPUs, 51 samples, 5 cost terms, 50 predicted obstacles, rows generated on device, fp64")
+    if name == "config4":
+        # multi-agent: 6 agents (the ego + the 5 cars of the T-junction fixture are agents in main_multiagent.py),
+        # 50,000 candidates each, own reference path / Frenet state / predictions (the others' motion) per agent
+        agents = []
+        for a in range(6):
+            poly = [syn.straight_polyline(400), syn.arc_polyline(R=80.0, M=400), syn.scurve_polyline(M=400),
+                    syn.arc_polyline(R=150.0, M=400, start_heading=0.5), syn.scurve_polyline(M=400, amp=3.0),
+                    syn.arc_polyline(R=60.0, M=400, start_heading=-0.3)][a]
+            v0 = 6.0 + a
+            x_cl = ([10.0 + 2 * a, v0, 0.1 * a], [0.1 * a - 0.2, 0.02 * a, 0.0])
+            v_lo, v_hi = syn.velocity_interval(v0, syn.VEHICLE_2["a_max"], 3.0, syn.VEHICLE_2["v_max"])
+            agents.append(dict(polyline=poly, x_cl=x_cl, v0=v0, x0_orientation=0.05 * a, v_des=v0 + 1.0,
+                               t1=np.round(np.arange(11, 31) * 0.1, 2), v1=np.linspace(v_lo, v_hi, 50),
+                               d1=np.linspace(-3.0, 3.0, 50), preds=syn.synthetic_predictions(poly, 5, 31, 0.1, seed=100 + a)))
+        return dict(agents=agents, N=30, dt=0.1, rows_per_rank=300_000, scaling="weak", preds=agents[0]["preds"],
+                    polyline=agents[0]["polyline"], x_cl=agents[0]["x_cl"], t1=agents[0]["t1"], v1=agents[0]["v1"],
+                    d1=agents[0]["d1"], x0_orientation=0.0, v_des=7.0, v0=6.0,
+                    label="configs[3]: 6 agents x 50,000 candidates (own reference path, state and 5 predicted obstacles "
+                          "each) batched into ONE eval-kernel launch, 31 samples, 5 cost terms, fp64")
     raise SystemExit(f"unknown workload {name}")
 
 
@@ -200,6 +219,64 @@ def run_reference_arm(args, w, S):
     print(json.dumps(line))
 
 
+def run_config4(args, w, local_rank):
+    """Multi-agent batch: one frx_plan_batched call per step (host matrices in, H2D inside)."""
+    import torch
+    from frenetix_motion_planner_b200 import _capi, hotpath
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device")
+    veh = syn.VEHICLE_2
+    names, weights = hotpath.active_costs(syn.DEFAULT_COST_WEIGHTS)
+    handlers, mats = [], []
+    for ag in w["agents"]:
+        h = _capi.Handler(local_rank)
+        cs = CoordinateSystem(ag["polyline"])
+        h.set_params(dt=w["dt"], N=w["N"], low_vel_mode=ag["v0"] < 2.0, draw_traj_set=True, kinematic_debug=True,
+                     a_max=veh["a_max"], v_switch=veh["v_switch"], delta_max=veh["delta_max"], wheelbase=veh["wheelbase"],
+                     wb_rear_axle=veh["wb_rear_axle"], length=veh["length"], width=veh["width"],
+                     x0_orientation=ag["x0_orientation"], desired_velocity=ag["v_des"], cost_names=names,
+                     cost_weights=weights)
+        h.set_reference(cs.ref_pos, cs.ref_theta, cs.ref_curv, cs.ref_curv_d, ag["polyline"][:, 0], ag["polyline"][:, 1])
+        h.set_time_tables(*hotpath.time_tables(np.unique(ag["t1"]), w["dt"], w["N"] + 1))
+        h.set_predictions(*hotpath.pack_predictions(ag["preds"]))
+        handlers.append(h)
+        mats.append(torch.from_numpy(syn.grid_sampling_matrix(ag["t1"], ag["v1"], ag["d1"], ag["x_cl"])).pin_memory().numpy())
+    rows = sum(m.shape[0] for m in mats)
+    for _ in range(args.warmup):
+        res = _capi.plan_batched(handlers, mats)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    kms = []
+    for _ in range(args.steps):
+        res = _capi.plan_batched(handlers, mats)
+        kms.append(res[0].eval_kernel_ms)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    # the same agents one after the other (what AgentBatch._step_agents does)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        solo = [h.plan(m) for h, m in zip(handlers, mats)]
+    dt_solo = time.perf_counter() - t0
+    same = all(a.argmin == b.argmin and a.min_cost == b.min_cost for a, b in zip(res, solo))
+    B_cand = algorithmic_bytes_per_candidate(w["N"] + 1, len(names), True)
+    peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]) if os.path.exists(
+        os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+    kmean = float(np.mean(kms))
+    ach = rows * B_cand / (kmean * 1e-3) / 1e9
+    print(json.dumps({
+        "metric": METRIC, "value": rows * args.steps / dt, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": w["label"], "agents": len(handlers), "rows_total": rows,
+                   "timing": "wall clock around frx_plan_batched (pinned host matrices in, H2D inside)",
+                   "sequential_plans_ms_per_step": dt_solo / args.steps * 1e3, "batched_equals_sequential": bool(same)},
+        "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                     "kernel": "frx_eval_batched_kernel", "kernel_ms": kmean, "algorithmic_bytes_per_candidate": B_cand},
+        "e2e": {"value": rows * args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": rows * 104,
+                "d2h_bytes_per_step": 152 * len(handlers)},
+        "gpu_launches": args.steps * (1 + 2 * len(handlers))}))
+
+
 # ----------------------------------------------------------------------------------------------
 # main
 # ----------------------------------------------------------------------------------------------
@@ -238,6 +315,9 @@ def main():
     import torch.distributed as dist
     from frenetix_motion_planner_b200 import _capi, hotpath
     from frenetix_motion_planner_b200.dist import ArgminExchange
+
+    if args.workload == "config4":
+        return run_config4(args, w, local_rank)
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback (use --impl reference for the CPU arm)")

@@ -64,7 +64,7 @@ class FrxResult(C.Structure):
 
 EXPORTS = ("frx_abi_version", "frx_create", "frx_destroy", "frx_last_error", "frx_set_reference", "frx_set_params",
            "frx_set_time_tables", "frx_set_predictions", "frx_set_obstacle_positions", "frx_set_static_obbs",
-           "frx_plan", "frx_plan_device", "frx_plan_grid", "frx_state_pitch", "frx_get_states",
+           "frx_plan", "frx_plan_device", "frx_plan_grid", "frx_plan_batched", "frx_state_pitch", "frx_get_states",
            "frx_get_states_range", "frx_get_costs", "frx_get_flags", "frx_device_pointers", "frx_winner_device_pointer",
            "frx_selftest_fdiv", "frx_set_stream",
            "frx_synchronize")
@@ -102,6 +102,7 @@ def load_library(path: Optional[str] = None):
     lib.frx_plan_device.argtypes = [vp, C.c_int64, vp, C.c_int64, C.POINTER(FrxResult)]
     lib.frx_plan_grid.argtypes = [vp, C.c_int32, dp, C.c_int32, dp, C.c_int32, dp, dp, C.c_int64, C.c_int64,
                                   C.POINTER(FrxResult)]
+    lib.frx_plan_batched.argtypes = [C.c_int32, C.POINTER(vp), C.POINTER(C.c_int64), C.POINTER(dp), C.POINTER(FrxResult)]
     lib.frx_state_pitch.argtypes = [vp]; lib.frx_state_pitch.restype = C.c_int32
     lib.frx_get_states.argtypes = [vp, C.c_int64, C.POINTER(C.c_int64), C.c_uint32, dp]
     lib.frx_get_states_range.argtypes = [vp, C.c_int64, C.c_int64, C.c_uint32, dp]
@@ -326,3 +327,26 @@ class Handler:
 
     def synchronize(self):
         self._check(self._lib.frx_synchronize(self._ctx))
+
+
+def plan_batched(handlers: Sequence["Handler"], samplings: Sequence[np.ndarray]):
+    """One eval-kernel launch for several planners (agents): -> list of FrxResult, one per handler."""
+    n = len(handlers)
+    if n == 0 or n != len(samplings):
+        raise ValueError("need one sampling matrix per handler")
+    lib = load_library()
+    mats = [np.ascontiguousarray(S, dtype=np.float64) for S in samplings]
+    for S in mats:
+        if S.ndim != 2 or S.shape[1] != 13:
+            raise ValueError("sampling matrix must be [N, 13]")
+    ctxs = (C.c_void_p * n)(*[h._ctx for h in handlers])
+    rows = (C.c_int64 * n)(*[S.shape[0] for S in mats])
+    ptrs = (C.POINTER(C.c_double) * n)(*[_dptr(S) for S in mats])
+    res = (FrxResult * n)()
+    rc = lib.frx_plan_batched(n, ctxs, rows, ptrs, res)
+    if rc != 0:
+        msg = lib.frx_last_error(handlers[0]._ctx)
+        raise FrxError(f"libfrx_b200 error {rc}: {msg.decode() if msg else '?'}")
+    for h, S in zip(handlers, mats):
+        h.n_rows = S.shape[0]
+    return list(res)

@@ -15,6 +15,8 @@
 size_t frx_eval_smem_bytes(int Mpad, int nchunk);
 cudaError_t frx_launch_eval(const FrxKernelArgs& a, int nchunk, int grid, cudaStream_t st);
 cudaError_t frx_eval_occupancy(int Mpad, int nchunk, int* blocks_per_sm);
+cudaError_t frx_launch_eval_batched(const FrxKernelArgs* d_agents, const int* d_cta_begin, int n_agents, int max_Mpad,
+                                    int nchunk, int grid, cudaStream_t st);
 void frx_launch_obstacle_prep(int O, int T, int Tp, const double* pos, const double* cov, const double* theta,
                               const double* hl, const double* hw, double* obs, cudaStream_t st);
 void frx_launch_static_prep(int B, const double* obb, double* out, cudaStream_t st);
@@ -71,6 +73,7 @@ struct frx_ctx {
     DevBuf<double> states, costs, total; DevBuf<uint32_t> flags; DevBuf<int> traj_len;
     DevBuf<FrxBest> blockbest, winner; DevBuf<unsigned long long> counters;
     DevBuf<long long> gidx; DevBuf<double> gout;
+    DevBuf<FrxKernelArgs> batch_args; DevBuf<int> batch_cta;
     HostResult* h_res = nullptr;
 
     long long lastN = 0; int lastK = 0; int lastNtp = 0;
@@ -136,7 +139,7 @@ int frx_destroy(frx_ctx* ctx) {
     ctx->raw_hl.release(); ctx->raw_hw.release(); ctx->obs_len.release(); ctx->obs_pos.release();
     ctx->sobb.release(); ctx->raw_sobb.release(); ctx->sampling.release(); ctx->grid.release();
     ctx->states.release(); ctx->costs.release(); ctx->total.release(); ctx->flags.release(); ctx->traj_len.release();
-    ctx->blockbest.release(); ctx->winner.release(); ctx->counters.release(); ctx->gidx.release(); ctx->gout.release();
+    ctx->blockbest.release(); ctx->winner.release(); ctx->counters.release(); ctx->gidx.release(); ctx->gout.release(); ctx->batch_args.release(); ctx->batch_cta.release();
     if (ctx->h_res) cudaFreeHost(ctx->h_res);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -271,31 +274,27 @@ int frx_set_static_obbs(frx_ctx* ctx, int32_t B, const double* obb) {
     return FRX_OK;
 }
 
-// common tail of the three plan entry points
-static int run_plan(frx_ctx* ctx, long long N, const double* d_sampling, bool grid_mode, int g_nv, int g_nd,
-                    const double* d_t1, const double* d_v1, const double* d_d1, const double* xcl,
-                    long long row_first, long long row_base, frx_result* out) {
+// ---- one plan = prepare (buffers + kernel arguments) -> launch -> finish (arg-min, read-back of the result)
+static int prepare_plan(frx_ctx* ctx, long long N, const double* d_sampling, bool grid_mode, int g_nv, int g_nd,
+                        const double* d_t1, const double* d_v1, const double* d_d1, const double* xcl,
+                        long long row_first, long long row_base, int max_grid, FrxKernelArgs* a_out, int* grid_out,
+                        int* nchunk_out) {
     REQUIRE(ctx->have_params && ctx->have_ref && ctx->have_tables,
             "frx_plan: frx_set_params, frx_set_reference and frx_set_time_tables must be called first");
-    REQUIRE(out != nullptr, "frx_plan: null result");
     const frx_params& p = ctx->prm;
     const int Nt = p.N + 1, Ntp = pitch_for(Nt), nchunk = nchunk_for(Nt), K = p.n_costs;
-    cudaStream_t st = ctx->stream;
-    memset(out, 0, sizeof(*out));
-    out->argmin = -1; out->min_cost = INFINITY; out->n_rows = N;
-
     if (p.store_states) CK(ctx->states.reserve((size_t)FRX_NUM_FIELDS * N * Ntp));
     CK(ctx->costs.reserve((size_t)N * (K > 0 ? K : 1))); CK(ctx->total.reserve(N)); CK(ctx->flags.reserve(N));
     CK(ctx->traj_len.reserve(N));
-
     if (ctx->occ_Mpad != ctx->Mpad || ctx->occ_nchunk != nchunk) {
         int b = 1;
         CK(frx_eval_occupancy(ctx->Mpad, nchunk, &b));
         REQUIRE(b >= 1, "frx_plan: eval kernel does not fit on an SM with this reference length");
         ctx->occ_blocks = b; ctx->occ_Mpad = ctx->Mpad; ctx->occ_nchunk = nchunk;
     }
-    long long want = (N + FRX_WARPS_PER_CTA - 1) / FRX_WARPS_PER_CTA;
-    long long full = (long long)ctx->sm_count * ctx->occ_blocks;
+    long long want = (N + FRX_CHUNK_ROWS - 1) / FRX_CHUNK_ROWS;       // one warp per chunk at most
+    want = (want + FRX_WARPS_PER_CTA - 1) / FRX_WARPS_PER_CTA;
+    long long full = (max_grid > 0) ? max_grid : (long long)ctx->sm_count * ctx->occ_blocks;
     int grid = (int)(want < full ? want : full);
     if (grid < 1) grid = 1;
     CK(ctx->blockbest.reserve(grid));
@@ -317,11 +316,14 @@ static int run_plan(frx_ctx* ctx, long long N, const double* d_sampling, bool gr
     a.row_first = row_first; a.row_base = row_base; a.N = N;
     a.states = ctx->states.p; a.costs = ctx->costs.p; a.total = ctx->total.p; a.flags = ctx->flags.p;
     a.traj_len = ctx->traj_len.p; a.blockbest = ctx->blockbest.p; a.counters = ctx->counters.p;
+    *a_out = a; *grid_out = grid; *nchunk_out = nchunk;
+    ctx->lastN = N; ctx->lastK = K; ctx->lastNtp = Ntp;
+    return FRX_OK;
+}
 
-    CK(cudaMemsetAsync(ctx->counters.p, 0, sizeof(unsigned long long) * FRX_NUM_COUNTERS, st));
-    CK(cudaEventRecord(ctx->evk0, st));
-    CK(frx_launch_eval(a, nchunk, grid, st));
-    CK(cudaEventRecord(ctx->evk1, st));
+// arg-min + collision counter + async read-back of the result record, all on stream `st`
+static int enqueue_finish(frx_ctx* ctx, long long N, long long row_base, int grid, cudaStream_t st) {
+    const frx_params& p = ctx->prm;
     frx_launch_argmin(ctx->blockbest.p, grid, row_base, ctx->winner.p, st);
     CK(cudaGetLastError());
     if (p.check_collisions && (ctx->O > 0 || ctx->B > 0)) {
@@ -333,10 +335,12 @@ static int run_plan(frx_ctx* ctx, long long N, const double* d_sampling, bool gr
     CK(cudaMemcpyAsync(&ctx->h_res->winner, ctx->winner.p, sizeof(FrxBest), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(ctx->h_res->counters, ctx->counters.p, sizeof(unsigned long long) * FRX_NUM_COUNTERS,
                        cudaMemcpyDeviceToHost, st));
-    CK(cudaEventRecord(ctx->ev1, st));
-    CK(cudaStreamSynchronize(st));
+    return FRX_OK;
+}
 
-    ctx->lastN = N; ctx->lastK = K; ctx->lastNtp = Ntp;
+static int fill_result(frx_ctx* ctx, long long N, frx_result* out) {
+    memset(out, 0, sizeof(*out));
+    out->n_rows = N;
     const HostResult& h = *ctx->h_res;
     if (h.counters[CNT_T_NOT_FOUND]) {
         ctx->err = "frx_plan: a sampling row uses a duration (column 1) that is missing from frx_set_time_tables";
@@ -352,6 +356,29 @@ static int run_plan(frx_ctx* ctx, long long N, const double* d_sampling, bool gr
     out->collision_counter = (int64_t)h.counters[CNT_COLLISION_COUNTER];
     out->reason_counts[0] = (int64_t)h.counters[CNT_INFEASIBLE_IN_LIST];
     for (int q = 1; q <= 10; ++q) out->reason_counts[q] = (int64_t)h.counters[CNT_REASON1 + q - 1];
+    return FRX_OK;
+}
+
+static int run_plan(frx_ctx* ctx, long long N, const double* d_sampling, bool grid_mode, int g_nv, int g_nd,
+                    const double* d_t1, const double* d_v1, const double* d_d1, const double* xcl,
+                    long long row_first, long long row_base, frx_result* out) {
+    REQUIRE(out != nullptr, "frx_plan: null result");
+    cudaStream_t st = ctx->stream;
+    FrxKernelArgs a;
+    int grid = 1, nchunk = 1;
+    int rc = prepare_plan(ctx, N, d_sampling, grid_mode, g_nv, g_nd, d_t1, d_v1, d_d1, xcl, row_first, row_base, 0, &a,
+                          &grid, &nchunk);
+    if (rc != FRX_OK) return rc;
+    CK(cudaMemsetAsync(ctx->counters.p, 0, sizeof(unsigned long long) * FRX_NUM_COUNTERS, st));
+    CK(cudaEventRecord(ctx->evk0, st));
+    CK(frx_launch_eval(a, nchunk, grid, st));
+    CK(cudaEventRecord(ctx->evk1, st));
+    rc = enqueue_finish(ctx, N, row_base, grid, st);
+    if (rc != FRX_OK) return rc;
+    CK(cudaEventRecord(ctx->ev1, st));
+    CK(cudaStreamSynchronize(st));
+    rc = fill_result(ctx, N, out);
+    if (rc != FRX_OK) return rc;
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, ctx->evk0, ctx->evk1)); out->eval_kernel_ms = ms;
     CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1)); out->total_device_ms = ms;
@@ -390,6 +417,74 @@ int frx_plan_grid(frx_ctx* ctx, int32_t nt, const double* t1, int32_t nv, const 
     CK(cudaMemcpyAsync(ctx->grid.p + nt + nv, d1, sizeof(double) * nd, cudaMemcpyHostToDevice, ctx->stream));
     return run_plan(ctx, row_count, nullptr, true, nv, nd, ctx->grid.p, ctx->grid.p + nt, ctx->grid.p + nt + nv, x_cl,
                     row_first, row_first, out);
+}
+
+int frx_plan_batched(int32_t n_agents, frx_ctx** ctxs, const int64_t* n_rows, const double* const* samplings,
+                     frx_result* results) {
+    if (n_agents < 1 || !ctxs || !n_rows || !samplings || !results || !ctxs[0]) return FRX_ERR_INVALID;
+    frx_ctx* ctx = ctxs[0];                       // the batch runs on the first context's stream
+    REQUIRE(n_agents <= 256, "frx_plan_batched: at most 256 agents per launch");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    std::vector<FrxKernelArgs> args(n_agents);
+    std::vector<int> cta_begin(n_agents + 1, 0), grids(n_agents, 1);
+    long long total_rows = 0;
+    int nchunk0 = -1, max_Mpad = 0, occ = 1;
+    for (int a = 0; a < n_agents; ++a) {
+        REQUIRE(ctxs[a] && ctxs[a]->device == ctx->device, "frx_plan_batched: all contexts must live on one device");
+        REQUIRE(n_rows[a] >= 1 && samplings[a], "frx_plan_batched: empty sampling matrix");
+        total_rows += n_rows[a];
+    }
+    CK(cudaEventRecord(ctx->ev0, st));
+    for (int a = 0; a < n_agents; ++a) {
+        frx_ctx* c = ctxs[a];
+        CK(c->sampling.reserve((size_t)n_rows[a] * 13));
+        CK(cudaMemcpyAsync(c->sampling.p, samplings[a], (size_t)n_rows[a] * 13 * sizeof(double), cudaMemcpyHostToDevice, st));
+    }
+    // CTA budget: the persistent grid of one launch, split over the agents in proportion to their rows
+    {
+        int nchunk = nchunk_for(ctx->prm.N + 1), b = 1;
+        for (int a = 0; a < n_agents; ++a) if (ctxs[a]->Mpad > max_Mpad) max_Mpad = ctxs[a]->Mpad;
+        CK(frx_eval_occupancy(max_Mpad, nchunk, &b));
+        REQUIRE(b >= 1, "frx_plan_batched: eval kernel does not fit on an SM");
+        occ = b;
+    }
+    const long long budget = (long long)ctx->sm_count * occ;
+    for (int a = 0; a < n_agents; ++a) {
+        frx_ctx* c = ctxs[a];
+        long long share = (budget * n_rows[a] + total_rows - 1) / total_rows;
+        if (share < 1) share = 1;
+        int g = 1, nch = 1;
+        int rc = prepare_plan(c, n_rows[a], c->sampling.p, false, 0, 0, nullptr, nullptr, nullptr, nullptr, 0, 0,
+                              (int)share, &args[a], &g, &nch);
+        if (rc != FRX_OK) { ctx->err = c->err; return rc; }
+        if (nchunk0 < 0) nchunk0 = nch;
+        REQUIRE(nch == nchunk0, "frx_plan_batched: all agents must share the planning horizon (samples per candidate)");
+        grids[a] = g;
+        cta_begin[a + 1] = cta_begin[a] + g;
+        CK(cudaMemsetAsync(c->counters.p, 0, sizeof(unsigned long long) * FRX_NUM_COUNTERS, st));
+    }
+    CK(ctx->batch_args.reserve(n_agents)); CK(ctx->batch_cta.reserve(n_agents + 1));
+    CK(cudaMemcpyAsync(ctx->batch_args.p, args.data(), sizeof(FrxKernelArgs) * n_agents, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->batch_cta.p, cta_begin.data(), sizeof(int) * (n_agents + 1), cudaMemcpyHostToDevice, st));
+    CK(cudaEventRecord(ctx->evk0, st));
+    CK(frx_launch_eval_batched(ctx->batch_args.p, ctx->batch_cta.p, n_agents, max_Mpad, nchunk0, cta_begin[n_agents], st));
+    CK(cudaEventRecord(ctx->evk1, st));
+    for (int a = 0; a < n_agents; ++a) {
+        int rc = enqueue_finish(ctxs[a], n_rows[a], 0, grids[a], st);
+        if (rc != FRX_OK) { ctx->err = ctxs[a]->err; return rc; }
+    }
+    CK(cudaEventRecord(ctx->ev1, st));
+    CK(cudaStreamSynchronize(st));     // pageable host matrices may be reused by the caller after return
+    float kms = 0.f, tms = 0.f;
+    CK(cudaEventElapsedTime(&kms, ctx->evk0, ctx->evk1));
+    CK(cudaEventElapsedTime(&tms, ctx->ev0, ctx->ev1));
+    for (int a = 0; a < n_agents; ++a) {
+        int rc = fill_result(ctxs[a], n_rows[a], &results[a]);
+        if (rc != FRX_OK) { ctx->err = ctxs[a]->err; return rc; }
+        results[a].eval_kernel_ms = kms; results[a].total_device_ms = tms;     // one launch serves all agents
+    }
+    return FRX_OK;
 }
 
 int32_t frx_state_pitch(const frx_ctx* ctx) { return ctx ? ctx->lastNtp : 0; }

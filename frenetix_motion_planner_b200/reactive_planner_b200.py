@@ -315,15 +315,18 @@ class ReactivePlannerB200:
                                             cpp_style=(self.sampling_style == "cpp"))
         return python_path_rows(t_set, v_set, d_set, self.x_cl)
 
-    def _evaluate(self, sampling: np.ndarray) -> Tuple[TrajectoryBundle, "hotpath.PlanOutput"]:
-        if self._bundle is not None:
-            self._bundle = None                  # device buffers are recycled by the next plan
+    def _prepare_level(self, samp_level: int) -> np.ndarray:
+        """Host work of one sampling level: the matrix and the time tables of its durations."""
+        sampling = self._sampling_matrix(samp_level)
+        self._total_count = sampling.shape[0]
+        self._bundle = None                      # device buffers are recycled by the next plan
         self.handler.set_time_tables(*hotpath.time_tables(hotpath.distinct_durations(sampling), self.dT, self.N + 1))
-        res = hotpath.PlanOutput.from_result(self.handler.plan(sampling))
-        bundle = TrajectoryBundle(self.handler, sampling.shape[0], self.cost_names, self.cost_weight_list, self.dT,
-                                  self.horizon, self.N + 1, self._LOW_VEL_MODE, sampling=sampling)
-        self._bundle = bundle
-        return bundle, res
+        return sampling
+
+    def _make_bundle(self, sampling: np.ndarray) -> TrajectoryBundle:
+        self._bundle = TrajectoryBundle(self.handler, sampling.shape[0], self.cost_names, self.cost_weight_list, self.dT,
+                                        self.horizon, self.N + 1, self._LOW_VEL_MODE, sampling=sampling)
+        return self._bundle
 
     def plan(self) -> tuple:
         """reactive_planner.py:67-130 with the per-candidate work on the device."""
@@ -331,14 +334,15 @@ class ReactivePlannerB200:
         t0 = time.time()
         self._push_static_inputs()
         samp_level = self._sampling_min
-        bundle = None
         while optimal_trajectory is None and samp_level < self._sampling_max:
-            sampling = self._sampling_matrix(samp_level)
-            self._total_count = sampling.shape[0]
-            bundle, res = self._evaluate(sampling)
-            optimal_trajectory = self._get_optimal_trajectory(bundle, res, samp_level)
+            sampling = self._prepare_level(samp_level)
+            res = hotpath.PlanOutput.from_result(self.handler.plan(sampling))
+            optimal_trajectory = self._get_optimal_trajectory(self._make_bundle(sampling), res, samp_level)
             samp_level += 1
-        planning_time = time.time() - t0
+        return self._finish_plan(optimal_trajectory, time.time() - t0)
+
+    def _finish_plan(self, optimal_trajectory, planning_time: float):
+        """reactive_planner.py:106-130: output conversion, stand-still fallback, post-processing."""
         self.trajectory_pair = self._compute_trajectory_pair(optimal_trajectory) if optimal_trajectory is not None else None
         if self.trajectory_pair is not None:
             self.set_ego_vehicle_state(self.convert_state_list_to_commonroad_object(self.trajectory_pair[0].state_list))
@@ -458,3 +462,36 @@ def hotpath_make_valid_orientation(angle: float) -> float:
     if np.pi <= angle <= two_pi:
         angle = angle - two_pi
     return angle
+
+
+def plan_batched(planners: List["ReactivePlannerB200"]) -> list:
+    """All agents of a multi-agent step in ONE eval-kernel launch per sampling level.
+
+    The reference steps its agents one after the other (cr_scenario_handler/simulation/agent_batch.py:186-189 ->
+    agent.py:236 -> planner.plan()).  Here every planner does its host-side preparation, then the sampling
+    matrices of all of them go through ``frx_plan_batched`` together, then every planner finishes its own
+    plan() (statistics, selection, output conversion).  Planners that found nothing re-enter the next round
+    with their next sampling level, exactly like the while-loop of reactive_planner.py:84-97.
+    Returns the trajectory pairs in the order of `planners`."""
+    t0 = time.time()
+    level, optimal = {}, {}
+    for p in planners:
+        p._push_static_inputs()
+        level[id(p)] = p._sampling_min
+    pending = [p for p in planners if level[id(p)] < p._sampling_max]
+    for p in planners:
+        optimal[id(p)] = None
+    while pending:
+        mats = [p._prepare_level(level[id(p)]) for p in pending]
+        results = _capi.plan_batched([p.handler for p in pending], mats)
+        nxt = []
+        for p, S, r in zip(pending, mats, results):
+            res = hotpath.PlanOutput.from_result(r)
+            opt = p._get_optimal_trajectory(p._make_bundle(S), res, level[id(p)])
+            level[id(p)] += 1
+            optimal[id(p)] = opt
+            if opt is None and level[id(p)] < p._sampling_max:
+                nxt.append(p)
+        pending = nxt
+    dt = time.time() - t0
+    return [p._finish_plan(optimal[id(p)], dt) for p in planners]

@@ -34,6 +34,8 @@
  *                                 generate_sampling_matrix would expand
  *                                 (frenetix_motion_planner/sampling_matrix.py:85-121)
  *   frx_plan_device               same as frx_plan with the sampling matrix already resident in HBM
+ *   frx_plan_batched              AgentBatch._step_agents: one launch for all agents' plan() calls
+ *                                 (cr_scenario_handler/simulation/agent_batch.py:186-189, agent.py:185-270)
  *   frx_get_*                     lazy read-back of what the reference keeps in TrajectorySample objects
  *                                 (frenetix_motion_planner/trajectories.py:56-478)
  *
@@ -151,6 +153,14 @@ int frx_plan_device(frx_ctx* ctx, int64_t N, const void* d_sampling, int64_t row
 int frx_plan_grid(frx_ctx* ctx, int32_t nt, const double* t1, int32_t nv, const double* ss1,
                   int32_t nd, const double* d1, const double* x_cl, int64_t row_first,
                   int64_t row_count, frx_result* out);
+
+/* Multi-agent batch (main_multiagent.py; cr_scenario_handler/simulation/agent_batch.py:186-189 loops
+ * agent.step_agent() one after the other): ONE eval-kernel launch evaluates the sampling matrices of all
+ * agents.  ctxs[a] is agent a's own context (reference path, params, predictions set as for frx_plan);
+ * all contexts must live on one device and share the planning horizon; the launch runs on ctxs[0]'s stream;
+ * results[a] is agent a's frx_result, read-back per context as usual. */
+int frx_plan_batched(int32_t n_agents, frx_ctx** ctxs, const int64_t* n_rows, const double* const* samplings,
+                     frx_result* results);
 
 /* read-back (rows are LOCAL indices of the last plan call) */
 int32_t frx_state_pitch(const frx_ctx* ctx);

@@ -107,3 +107,31 @@ def test_resampling_loop_and_last_level_fallback():
     p.risk_function = lambda t: -t.cost                             # user-supplied risk: prefers the most expensive
     p.plan()
     assert p.optimal_trajectory.cost == p._bundle.total[(p._bundle.flags & 3) == 3].max()
+
+
+def test_multi_agent_batched_launch_equals_individual_plans():
+    """BASELINE.json configs[3] shape (several agents, own reference path / state / predictions each):
+    one batched launch must give every agent exactly what its own plan() gives."""
+    from frenetix_motion_planner_b200.reactive_planner_b200 import plan_batched
+    cases = [("arc_hv_draw_pred", 9.5), ("straight_hv_draw", 8.0), ("scurve_lowvel_draw", 1.2), ("short_hv_draw", 8.0),
+             ("scurve_brake_hv_draw", 3.0)]
+    solo, batch = [], []
+    for name, v0 in cases:
+        g, ref, prm, preds = load_golden(name)
+        for lst in (solo, batch):
+            p = make_planner(g, prm, preds, v0)
+            p.collision_check_enabled = True
+            lst.append(p)
+    for p in solo:
+        p.plan()
+    pairs = plan_batched(batch)
+    assert len(pairs) == len(cases) and all(pr is not None for pr in pairs)
+    for a, b in zip(solo, batch):
+        assert a.optimal_trajectory.uniqueId == b.optimal_trajectory.uniqueId
+        assert a.optimal_trajectory.cost == b.optimal_trajectory.cost
+        assert a._infeasible_count_kinematics == b._infeasible_count_kinematics
+        assert a.infeasible_count_collision == b.infeasible_count_collision
+        assert np.array_equal(a._bundle.flags, b._bundle.flags) and np.array_equal(a._bundle.total, b._bundle.total)
+        rows = np.arange(0, a._bundle.n_rows, 37)
+        assert np.array_equal(a._bundle.states(rows), b._bundle.states(rows))
+        assert [t.uniqueId for t in a.all_traj[:50]] == [t.uniqueId for t in b.all_traj[:50]]
