@@ -15,8 +15,8 @@
 size_t frx_eval_smem_bytes(int Mpad, int nchunk);
 cudaError_t frx_launch_eval(const FrxKernelArgs& a, int nchunk, int grid, cudaStream_t st);
 cudaError_t frx_eval_occupancy(int Mpad, int nchunk, int* blocks_per_sm);
-cudaError_t frx_launch_eval_batched(const FrxKernelArgs* d_agents, const int* d_cta_begin, int n_agents, int max_Mpad,
-                                    int nchunk, int grid, cudaStream_t st);
+cudaError_t frx_launch_eval_batched(const FrxKernelArgs* h_agents, const FrxKernelArgs* d_agents, const int* d_cta_begin,
+                                    int n_agents, int max_Mpad, int nchunk, int grid, cudaStream_t st);
 void frx_launch_obstacle_prep(int O, int T, int Tp, const double* pos, const double* cov, const double* theta,
                               const double* hl, const double* hw, double* obs, cudaStream_t st);
 void frx_launch_static_prep(int B, const double* obb, double* out, cudaStream_t st);
@@ -227,11 +227,9 @@ int frx_set_predictions(frx_ctx* ctx, int32_t O, int32_t T, const double* pos, c
     REQUIRE(T >= 1 && pos && cov && theta && half_len && half_wid && len_valid, "frx_set_predictions: bad arguments");
     for (int o = 0; o < O; ++o) REQUIRE(len_valid[o] >= 0 && len_valid[o] <= T, "frx_set_predictions: len_valid out of range");
     CK(cudaSetDevice(ctx->device));
-    const int Tp = (T + 3) & ~3;
     const size_t n = (size_t)O * T;
     CK(ctx->raw_pos.reserve(n * 2)); CK(ctx->raw_cov.reserve(n * 4)); CK(ctx->raw_theta.reserve(n));
     CK(ctx->raw_hl.reserve(O)); CK(ctx->raw_hw.reserve(O)); CK(ctx->obs_len.reserve(O));
-    CK(ctx->obs.reserve((size_t)O * FRX_OBS_NARR * Tp));
     cudaStream_t st = ctx->stream;
     CK(cudaMemcpyAsync(ctx->raw_pos.p, pos, n * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(ctx->raw_cov.p, cov, n * 4 * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -239,14 +237,13 @@ int frx_set_predictions(frx_ctx* ctx, int32_t O, int32_t T, const double* pos, c
     CK(cudaMemcpyAsync(ctx->raw_hl.p, half_len, O * sizeof(double), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(ctx->raw_hw.p, half_wid, O * sizeof(double), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(ctx->obs_len.p, len_valid, O * sizeof(int), cudaMemcpyHostToDevice, st));
-    CK(cudaMemsetAsync(ctx->obs.p, 0, (size_t)O * FRX_OBS_NARR * Tp * sizeof(double), st));
-    frx_launch_obstacle_prep(O, T, Tp, ctx->raw_pos.p, ctx->raw_cov.p, ctx->raw_theta.p, ctx->raw_hl.p, ctx->raw_hw.p,
-                             ctx->obs.p, st);
-    CK(cudaGetLastError());
     CK(cudaStreamSynchronize(st));   // host buffers may be pageable and reused by the caller
-    ctx->O = O; ctx->T = T; ctx->Tp = Tp;
+    // the SoA table (inverse covariances, hulls) is built at plan time, when the step pitch (32 x chunks of the
+    // planning horizon) is known
+    ctx->O = O; ctx->T = T; ctx->Tp = 0;
     return FRX_OK;
 }
+
 
 int frx_set_obstacle_positions(frx_ctx* ctx, int32_t n, const double* pos_xy) {
     if (!ctx) return FRX_ERR_INVALID;
@@ -277,8 +274,8 @@ int frx_set_static_obbs(frx_ctx* ctx, int32_t B, const double* obb) {
 // ---- one plan = prepare (buffers + kernel arguments) -> launch -> finish (arg-min, read-back of the result)
 static int prepare_plan(frx_ctx* ctx, long long N, const double* d_sampling, bool grid_mode, int g_nv, int g_nd,
                         const double* d_t1, const double* d_v1, const double* d_d1, const double* xcl,
-                        long long row_first, long long row_base, int max_grid, FrxKernelArgs* a_out, int* grid_out,
-                        int* nchunk_out) {
+                        long long row_first, long long row_base, int max_grid, cudaStream_t st, FrxKernelArgs* a_out,
+                        int* grid_out, int* nchunk_out) {
     REQUIRE(ctx->have_params && ctx->have_ref && ctx->have_tables,
             "frx_plan: frx_set_params, frx_set_reference and frx_set_time_tables must be called first");
     const frx_params& p = ctx->prm;
@@ -292,8 +289,16 @@ static int prepare_plan(frx_ctx* ctx, long long N, const double* d_sampling, boo
         REQUIRE(b >= 1, "frx_plan: eval kernel does not fit on an SM with this reference length");
         ctx->occ_blocks = b; ctx->occ_Mpad = ctx->Mpad; ctx->occ_nchunk = nchunk;
     }
-    long long want = (N + FRX_CHUNK_ROWS - 1) / FRX_CHUNK_ROWS;       // one warp per chunk at most
-    want = (want + FRX_WARPS_PER_CTA - 1) / FRX_WARPS_PER_CTA;
+    if (ctx->O > 0 && ctx->Tp != nchunk * 32) {      // (re)build the obstacle table for this horizon
+        const int Tp = nchunk * 32;
+        CK(ctx->obs.reserve((size_t)ctx->O * FRX_OBS_NARR * Tp));
+        CK(cudaMemsetAsync(ctx->obs.p, 0, (size_t)ctx->O * FRX_OBS_NARR * Tp * sizeof(double), st));
+        frx_launch_obstacle_prep(ctx->O, ctx->T, Tp, ctx->raw_pos.p, ctx->raw_cov.p, ctx->raw_theta.p, ctx->raw_hl.p,
+                                 ctx->raw_hw.p, ctx->obs.p, st);
+        CK(cudaGetLastError());
+        ctx->Tp = Tp;
+    }
+    long long want = (N + FRX_WARPS_PER_CTA - 1) / FRX_WARPS_PER_CTA;   // at least one row per warp
     long long full = (max_grid > 0) ? max_grid : (long long)ctx->sm_count * ctx->occ_blocks;
     int grid = (int)(want < full ? want : full);
     if (grid < 1) grid = 1;
@@ -366,7 +371,7 @@ static int run_plan(frx_ctx* ctx, long long N, const double* d_sampling, bool gr
     cudaStream_t st = ctx->stream;
     FrxKernelArgs a;
     int grid = 1, nchunk = 1;
-    int rc = prepare_plan(ctx, N, d_sampling, grid_mode, g_nv, g_nd, d_t1, d_v1, d_d1, xcl, row_first, row_base, 0, &a,
+    int rc = prepare_plan(ctx, N, d_sampling, grid_mode, g_nv, g_nd, d_t1, d_v1, d_d1, xcl, row_first, row_base, 0, st, &a,
                           &grid, &nchunk);
     if (rc != FRX_OK) return rc;
     CK(cudaMemsetAsync(ctx->counters.p, 0, sizeof(unsigned long long) * FRX_NUM_COUNTERS, st));
@@ -456,7 +461,7 @@ int frx_plan_batched(int32_t n_agents, frx_ctx** ctxs, const int64_t* n_rows, co
         if (share < 1) share = 1;
         int g = 1, nch = 1;
         int rc = prepare_plan(c, n_rows[a], c->sampling.p, false, 0, 0, nullptr, nullptr, nullptr, nullptr, 0, 0,
-                              (int)share, &args[a], &g, &nch);
+                              (int)share, st, &args[a], &g, &nch);
         if (rc != FRX_OK) { ctx->err = c->err; return rc; }
         if (nchunk0 < 0) nchunk0 = nch;
         REQUIRE(nch == nchunk0, "frx_plan_batched: all agents must share the planning horizon (samples per candidate)");
@@ -468,7 +473,7 @@ int frx_plan_batched(int32_t n_agents, frx_ctx** ctxs, const int64_t* n_rows, co
     CK(cudaMemcpyAsync(ctx->batch_args.p, args.data(), sizeof(FrxKernelArgs) * n_agents, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(ctx->batch_cta.p, cta_begin.data(), sizeof(int) * (n_agents + 1), cudaMemcpyHostToDevice, st));
     CK(cudaEventRecord(ctx->evk0, st));
-    CK(frx_launch_eval_batched(ctx->batch_args.p, ctx->batch_cta.p, n_agents, max_Mpad, nchunk0, cta_begin[n_agents], st));
+    CK(frx_launch_eval_batched(args.data(), ctx->batch_args.p, ctx->batch_cta.p, n_agents, max_Mpad, nchunk0, cta_begin[n_agents], st));
     CK(cudaEventRecord(ctx->evk1, st));
     for (int a = 0; a < n_agents; ++a) {
         int rc = enqueue_finish(ctxs[a], n_rows[a], 0, grids[a], st);

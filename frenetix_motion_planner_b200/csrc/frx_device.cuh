@@ -12,6 +12,9 @@
 #ifndef FRX_CHUNK_ROWS
 #define FRX_CHUNK_ROWS 8
 #endif
+#ifndef FRX_GUIDED
+#define FRX_GUIDED 0     // 1: chunk sizes shrink towards the end of the row range (guided self-scheduling)
+#endif
 #define FRX_EPS 1e-5
 
 // obstacle table, SoA with step pitch Tp: arr[(o * FRX_OBS_NARR + k) * Tp + t]
