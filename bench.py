@@ -311,6 +311,7 @@ def main():
             run_reference_arm(args, w, S)
         return
 
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep stdout to the one JSON line
     import torch
     import torch.distributed as dist
     from frenetix_motion_planner_b200 import _capi, hotpath
@@ -393,6 +394,9 @@ def main():
         if rank == 0:
             sampler.start()
             time.sleep(0.25)
+        if world > 1:
+            dist.barrier()                        # all ranks enter the timed loop together
+        torch.cuda.synchronize()
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
         kern_ms = []
         launches["n"] = 0
