@@ -44,10 +44,11 @@ def build_workload(name: str, world: int):
         x_cl = ([10.0, 8.0, 0.0], [0.2, 0.0, 0.0])
         t1 = np.round(np.arange(11, 31) * 0.1, 2)
         v_lo, v_hi = syn.velocity_interval(8.0, syn.VEHICLE_2["a_max"], 3.0, syn.VEHICLE_2["v_max"])
-        v1 = np.linspace(v_lo, v_hi, 50 * world)            # weak scaling: denser v axis, 50k rows per rank
+        scale = int(os.environ.get("FRX_BENCH_SCALE", "1"))   # tuning aid: N-times more rows per GPU (not the headline)
+        v1 = np.linspace(v_lo, v_hi, 50 * world * scale)     # weak scaling: denser v axis, 50k rows per rank
         d1 = np.linspace(-3.0, 3.0, 50)
         return dict(polyline=poly, x_cl=x_cl, t1=t1, v1=v1, d1=d1, N=30, dt=0.1, x0_orientation=0.0, v_des=8.0,
-                    v0=8.0, preds=[], rows_per_rank=50_000, scaling="weak",
+                    v0=8.0, preds=[], rows_per_rank=50_000 * scale, scaling="weak",
                     label="configs[1]: straight ref path (M=400), 20t x 50v x 50d = 50,000 candidates per GPU, "
                           "31 samples, 5 cost terms, 0 obstacles, fp64")
     if name == "config3":
@@ -274,7 +275,7 @@ def run_config4(args, w, local_rank):
                      "kernel": "frx_eval_batched_kernel", "kernel_ms": kmean, "algorithmic_bytes_per_candidate": B_cand},
         "e2e": {"value": rows * args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": rows * 104,
                 "d2h_bytes_per_step": 152 * len(handlers)},
-        "gpu_launches": args.steps * (1 + 2 * len(handlers))}))
+        "gpu_launches": args.steps * (1 + len(handlers))}))
 
 
 # ----------------------------------------------------------------------------------------------
@@ -357,7 +358,7 @@ def main():
     l2_flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 
     launches = {"n": 0}
-    n_aux = 1 + (1 if (packed is not None) else 0)      # argmin (+ collision counter) kernels per step
+    n_aux = 1 if (packed is not None) else 0           # collision-counter kernel (the arg-min runs in the eval kernel's last CTA)
 
     def step_resident():
         if grid_mode:

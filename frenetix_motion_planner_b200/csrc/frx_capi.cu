@@ -12,7 +12,7 @@
 #include "frx_device.cuh"
 
 // launchers implemented in frx_kernels.cu
-size_t frx_eval_smem_bytes(int Mpad, int nchunk);
+size_t frx_eval_smem_bytes(int Mpad, int nchunk, bool obs);
 cudaError_t frx_launch_eval(const FrxKernelArgs& a, int nchunk, int grid, cudaStream_t st);
 cudaError_t frx_eval_occupancy(int Mpad, int nchunk, int* blocks_per_sm);
 cudaError_t frx_launch_eval_batched(const FrxKernelArgs* h_agents, const FrxKernelArgs* d_agents, const int* d_cta_begin,
@@ -30,10 +30,7 @@ void frx_launch_selftest_fdiv(long long n, const double* a, const double* b, dou
 
 namespace {
 
-struct HostResult {
-    FrxBest winner;
-    unsigned long long counters[FRX_NUM_COUNTERS];
-};
+typedef FrxHostResult HostResult;   // written by the eval kernel's last CTA into mapped host memory
 
 template <typename T>
 struct DevBuf {
@@ -74,7 +71,9 @@ struct frx_ctx {
     DevBuf<FrxBest> blockbest, winner; DevBuf<unsigned long long> counters;
     DevBuf<long long> gidx; DevBuf<double> gout;
     DevBuf<FrxKernelArgs> batch_args; DevBuf<int> batch_cta;
-    HostResult* h_res = nullptr;
+    HostResult* h_res = nullptr;       // pinned + mapped
+    HostResult* d_res = nullptr;       // device address of h_res
+    bool counters_dirty = true;        // counters must be zeroed before the next launch (first use / after an error)
 
     long long lastN = 0; int lastK = 0; int lastNtp = 0;
     int occ_Mpad = -1, occ_nchunk = -1, occ_blocks = 1;
@@ -121,7 +120,12 @@ int frx_create(int device_ordinal, frx_ctx** out) {
     if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return FRX_ERR_CUDA; }
     ctx->stream = ctx->own_stream;
     cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1); cudaEventCreate(&ctx->evk0); cudaEventCreate(&ctx->evk1);
-    if (cudaMallocHost(&ctx->h_res, sizeof(HostResult)) != cudaSuccess) { frx_destroy(ctx); return FRX_ERR_NOMEM; }
+    if (cudaHostAlloc((void**)&ctx->h_res, sizeof(HostResult), cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer((void**)&ctx->d_res, ctx->h_res, 0) != cudaSuccess) {
+        frx_destroy(ctx);
+        return FRX_ERR_NOMEM;
+    }
+    memset(ctx->h_res, 0, sizeof(HostResult));
     if (ctx->winner.reserve(1) != cudaSuccess || ctx->counters.reserve(FRX_NUM_COUNTERS) != cudaSuccess) {
         frx_destroy(ctx);
         return FRX_ERR_NOMEM;
@@ -171,7 +175,7 @@ int frx_set_reference(frx_ctx* ctx, int32_t M, const double* ref_pos, const doub
     REQUIRE(M >= 2 && ref_pos && ref_theta && ref_curv && ref_curv_d && ref_x && ref_y, "frx_set_reference: bad arguments");
     CK(cudaSetDevice(ctx->device));
     int Mpad = (M + 1) & ~1;
-    REQUIRE(frx_eval_smem_bytes(Mpad, 2) <= (size_t)ctx->max_smem_optin,
+    REQUIRE(frx_eval_smem_bytes(Mpad, 2, true) <= (size_t)ctx->max_smem_optin,
             "frx_set_reference: reference path too long for the shared-memory table");
     std::vector<double> h((size_t)6 * Mpad, 0.0);
     const double* src[6] = {ref_pos, ref_theta, ref_curv, ref_curv_d, ref_x, ref_y};
@@ -321,25 +325,29 @@ static int prepare_plan(frx_ctx* ctx, long long N, const double* d_sampling, boo
     a.row_first = row_first; a.row_base = row_base; a.N = N;
     a.states = ctx->states.p; a.costs = ctx->costs.p; a.total = ctx->total.p; a.flags = ctx->flags.p;
     a.traj_len = ctx->traj_len.p; a.blockbest = ctx->blockbest.p; a.counters = ctx->counters.p;
+    a.winner = ctx->winner.p; a.host_res = ctx->d_res; a.n_cta = grid;
+    if (ctx->counters_dirty) {
+        CK(cudaMemsetAsync(ctx->counters.p, 0, sizeof(unsigned long long) * FRX_NUM_COUNTERS, st));
+        ctx->counters_dirty = false;
+    }
     *a_out = a; *grid_out = grid; *nchunk_out = nchunk;
     ctx->lastN = N; ctx->lastK = K; ctx->lastNtp = Ntp;
     return FRX_OK;
 }
 
-// arg-min + collision counter + async read-back of the result record, all on stream `st`
+// The eval kernel's last CTA already reduced the winners and wrote the result record to mapped host memory;
+// only Planner._collision_counter (needs the winner first, then one pass over the flags) is a second kernel.
 static int enqueue_finish(frx_ctx* ctx, long long N, long long row_base, int grid, cudaStream_t st) {
+    (void)grid;
     const frx_params& p = ctx->prm;
-    frx_launch_argmin(ctx->blockbest.p, grid, row_base, ctx->winner.p, st);
-    CK(cudaGetLastError());
     if (p.check_collisions && (ctx->O > 0 || ctx->B > 0)) {
         long long cg = (N + 255) / 256;
         if (cg > (long long)ctx->sm_count * 4) cg = (long long)ctx->sm_count * 4;
         frx_launch_collision_counter(N, row_base, ctx->total.p, ctx->flags.p, ctx->winner.p, ctx->counters.p, (int)cg, st);
         CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(&ctx->h_res->counters[CNT_COLLISION_COUNTER], ctx->counters.p + CNT_COLLISION_COUNTER,
+                           sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     }
-    CK(cudaMemcpyAsync(&ctx->h_res->winner, ctx->winner.p, sizeof(FrxBest), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(ctx->h_res->counters, ctx->counters.p, sizeof(unsigned long long) * FRX_NUM_COUNTERS,
-                       cudaMemcpyDeviceToHost, st));
     return FRX_OK;
 }
 
@@ -374,7 +382,7 @@ static int run_plan(frx_ctx* ctx, long long N, const double* d_sampling, bool gr
     int rc = prepare_plan(ctx, N, d_sampling, grid_mode, g_nv, g_nd, d_t1, d_v1, d_d1, xcl, row_first, row_base, 0, st, &a,
                           &grid, &nchunk);
     if (rc != FRX_OK) return rc;
-    CK(cudaMemsetAsync(ctx->counters.p, 0, sizeof(unsigned long long) * FRX_NUM_COUNTERS, st));
+    ctx->counters_dirty = true;          // cleared again once the launch sequence has completed
     CK(cudaEventRecord(ctx->evk0, st));
     CK(frx_launch_eval(a, nchunk, grid, st));
     CK(cudaEventRecord(ctx->evk1, st));
@@ -382,6 +390,7 @@ static int run_plan(frx_ctx* ctx, long long N, const double* d_sampling, bool gr
     if (rc != FRX_OK) return rc;
     CK(cudaEventRecord(ctx->ev1, st));
     CK(cudaStreamSynchronize(st));
+    ctx->counters_dirty = false;         // the last CTA re-armed them
     rc = fill_result(ctx, N, out);
     if (rc != FRX_OK) return rc;
     float ms = 0.f;
@@ -467,7 +476,7 @@ int frx_plan_batched(int32_t n_agents, frx_ctx** ctxs, const int64_t* n_rows, co
         REQUIRE(nch == nchunk0, "frx_plan_batched: all agents must share the planning horizon (samples per candidate)");
         grids[a] = g;
         cta_begin[a + 1] = cta_begin[a] + g;
-        CK(cudaMemsetAsync(c->counters.p, 0, sizeof(unsigned long long) * FRX_NUM_COUNTERS, st));
+        c->counters_dirty = true;
     }
     CK(ctx->batch_args.reserve(n_agents)); CK(ctx->batch_cta.reserve(n_agents + 1));
     CK(cudaMemcpyAsync(ctx->batch_args.p, args.data(), sizeof(FrxKernelArgs) * n_agents, cudaMemcpyHostToDevice, st));
@@ -481,6 +490,7 @@ int frx_plan_batched(int32_t n_agents, frx_ctx** ctxs, const int64_t* n_rows, co
     }
     CK(cudaEventRecord(ctx->ev1, st));
     CK(cudaStreamSynchronize(st));     // pageable host matrices may be reused by the caller after return
+    for (int a = 0; a < n_agents; ++a) ctxs[a]->counters_dirty = false;
     float kms = 0.f, tms = 0.f;
     CK(cudaEventElapsedTime(&kms, ctx->evk0, ctx->evk1));
     CK(cudaEventElapsedTime(&tms, ctx->ev0, ctx->ev1));

@@ -31,12 +31,19 @@ enum {
     CNT_COLLISION_COUNTER = CNT_REASON1 + 10,
     CNT_T_NOT_FOUND,
     CNT_WORK,          // chunk ticket counter of the eval kernel's dynamic scheduler
+    CNT_DONE,          // CTAs of this plan that have finished (last one publishes the result)
     FRX_NUM_COUNTERS
 };
 
 struct FrxBest {
     double cost;
     long long idx;
+};
+
+// result record the eval kernel's last CTA writes into mapped (pinned) host memory
+struct FrxHostResult {
+    FrxBest winner;
+    unsigned long long counters[FRX_NUM_COUNTERS];
 };
 
 struct FrxKernelArgs {
@@ -78,6 +85,9 @@ struct FrxKernelArgs {
     double* total;          // [N]
     uint32_t* flags;        // [N]
     int* traj_len;          // [N]
-    FrxBest* blockbest;     // [gridDim.x]
+    FrxBest* blockbest;     // [n_cta]
     unsigned long long* counters;
+    FrxBest* winner;        // device copy of the winner record (multi-GPU exchange payload)
+    FrxHostResult* host_res;// device address of the mapped host result struct
+    int n_cta;              // CTAs working on this plan (grid size, or this agent's share of a batched grid)
 };
