@@ -6,14 +6,14 @@
 #define FRX_WARPS_PER_CTA 4
 #define FRX_THREADS (FRX_WARPS_PER_CTA * 32)
 #ifndef FRX_MIN_CTAS
-#define FRX_MIN_CTAS 4   // resident CTAs per SM the eval kernel is compiled for (register cap 128)
+#define FRX_MIN_CTAS 5   // resident CTAs per SM the 32-step eval kernel is compiled for (register cap 102)
 #endif
 #define FRX_MAX_T_VALUES 128
 #ifndef FRX_CHUNK_ROWS
 #define FRX_CHUNK_ROWS 8
 #endif
 #ifndef FRX_GUIDED
-#define FRX_GUIDED 0     // 1: chunk sizes shrink towards the end of the row range (guided self-scheduling)
+#define FRX_GUIDED 1     // 1: chunk sizes shrink towards the end of the row range (guided self-scheduling)
 #endif
 #define FRX_EPS 1e-5
 
