@@ -94,10 +94,12 @@ FIELDS_CART = ("x", "y", "theta", "v", "a", "kappa", "kappa_dot")
 FIELDS_CL = ("s", "d", "theta", "s_dot", "s_ddot", "d_dot", "d_ddot")
 
 
-def run_case(name, polyline, x_cl, v0, th0, v_des, draw, debug, n_obs, cost_weights=None, seed=7):
+def run_case(name, polyline, x_cl, v0, th0, v_des, draw, debug, n_obs, cost_weights=None, seed=7, preds_list=None):
     cost_weights = cost_weights or syn.DEFAULT_COST_WEIGHTS
     Nt = 31
-    preds_list = syn.synthetic_predictions(polyline, n_obs, 31, 0.1, seed) if n_obs else []
+    if preds_list is None:
+        preds_list = syn.synthetic_predictions(polyline, n_obs, 31, 0.1, seed) if n_obs else []
+    n_obs = len(preds_list)
     predictions = {100 + i: p for i, p in enumerate(preds_list)}
     pl = build_planner(polyline, x_cl, v0, th0, v_des, draw, debug, predictions, cost_weights)
 
@@ -223,7 +225,37 @@ def inactive_cost_case():
     print("inactive costs ok")
 
 
+def tjunction_inputs():
+    """Inputs of the ZAM_Tjunction-1_42_T-1 fixture (tests/golden/tjunction.npz): smoothed reference path, the
+    ego's Frenet state at time step 0 and the ground-truth predictions of the five cars."""
+    g = np.load(os.path.join(HERE, "tjunction.npz"))
+    poly = g["reference_path"]
+    cs = CoordinateSystem(poly)
+    from frenetix_motion_planner_b200.reactive_planner_b200 import ReactivePlannerB200
+    x_0 = types.SimpleNamespace(position=g["ego_position_rear"], orientation=float(g["ego_orientation"]),
+                                velocity=float(g["ego_velocity"]), acceleration=float(g["ego_acceleration"]),
+                                yaw_rate=float(g["ego_yaw_rate"]), steering_angle=0.0, time_step=0)
+    me = types.SimpleNamespace(coordinate_system=cs, vehicle_params=types.SimpleNamespace(**syn.VEHICLE_2),
+                               _LOW_VEL_MODE=x_0.velocity < 2.0)
+    x_cl = ReactivePlannerB200._compute_initial_states(me, x_0)
+    x_cl = ([float(v) for v in x_cl[0]], [float(v) for v in x_cl[1]])
+    preds = []
+    for o in range(g["obstacle_states"].shape[0]):
+        st = g["obstacle_states"][o, 1:32]                       # time steps 1..31 (prediction_helpers.py:239-247)
+        preds.append({"pos_list": st[:, :2].copy(), "cov_list": np.tile(np.array([[0.1, 0.0], [0.0, 0.1]]), (31, 1, 1)),
+                      "orientation_list": st[:, 2].copy(), "v_list": st[:, 3].copy(),
+                      "shape": {"length": float(g["obstacle_shapes"][o, 0]) + 0.5,
+                                "width": float(g["obstacle_shapes"][o, 1]) + 0.2}})
+    return poly, x_cl, x_0, preds
+
+
 if __name__ == "__main__":
+    if "--tjunction" in sys.argv:
+        poly, x_cl, x_0, preds = tjunction_inputs()
+        print("x_cl", x_cl)
+        run_case("tjunction_draw", poly, x_cl, x_0.velocity, x_0.orientation, 8.0, True, True, 0, preds_list=preds)
+        run_case("tjunction_nodraw", poly, x_cl, x_0.velocity, x_0.orientation, 8.0, False, False, 0, preds_list=preds)
+        sys.exit(0)
     straight = syn.straight_polyline(200)
     arc = syn.arc_polyline(R=60.0, M=220)
     scurve = syn.scurve_polyline(M=220)

@@ -11,7 +11,10 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 GOLDEN_CASES = ["straight_hv_draw", "arc_hv_draw_pred", "arc_hv_nodraw_nodebug", "arc_hv_nodraw_debug",
                 "scurve_lowvel_draw", "scurve_lowvel_nodraw", "scurve_slow_hv_draw", "scurve_slow_hv_nodraw",
                 "scurve_brake_hv_draw", "scurve_brake_hv_nodraw_debug", "scurve_brake_hv_nodraw_nodebug",
-                "short_hv_draw", "short_hv_nodraw"]
+                "short_hv_draw", "short_hv_nodraw",
+                # ZAM_Tjunction-1_42_T-1 (BASELINE.json configs[0]): reference path, ego state and predicted cars
+                # of the shipped scenario (tests/golden/make_tjunction_fixture.py)
+                "tjunction_draw", "tjunction_nodraw"]
 
 
 def load_golden(name):

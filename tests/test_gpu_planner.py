@@ -135,3 +135,28 @@ def test_multi_agent_batched_launch_equals_individual_plans():
         rows = np.arange(0, a._bundle.n_rows, 37)
         assert np.array_equal(a._bundle.states(rows), b._bundle.states(rows))
         assert [t.uniqueId for t in a.all_traj[:50]] == [t.uniqueId for t in b.all_traj[:50]]
+
+
+def test_tjunction_scenario_from_cartesian_state():
+    """BASELINE.json configs[0]: the shipped ZAM_Tjunction-1_42_T-1 scenario.  The planner gets the ego's
+    CARTESIAN state (rear axle) and derives the Frenet state itself (planner.py:567-635), then plans."""
+    import os
+    from helpers import GOLDEN_DIR
+    fx = np.load(os.path.join(GOLDEN_DIR, "tjunction.npz"))
+    g, ref, prm, preds = load_golden("tjunction_draw")
+    p = make_planner(g, prm, preds, float(fx["ego_velocity"]))
+    x_0 = SimpleNamespace(position=fx["ego_position_rear"], orientation=float(fx["ego_orientation"]),
+                          velocity=float(fx["ego_velocity"]), acceleration=float(fx["ego_acceleration"]),
+                          yaw_rate=float(fx["ego_yaw_rate"]), steering_angle=0.0, time_step=0)
+    p.x_cl = None
+    p.update_externals(reference_path=fx["reference_path"], x_0=x_0, x_cl=None, desired_velocity=8.0)
+    assert np.allclose(p.x_cl[0], g["x_cl_lon"], rtol=1e-12) and np.allclose(p.x_cl[1], g["x_cl_lat"], rtol=1e-12)
+    p.plan()
+    ok = fo.plan(g["sampling"], ref, prm, preds, collision_check=False)["margins"] >= BAND
+    opt = p.optimal_trajectory
+    assert (opt.uniqueId == int(g["optimal_id"])) or not ok[opt.uniqueId] or not ok[int(g["optimal_id"])]
+    # with the collision sweep switched on the five predicted cars are checked as well
+    p.collision_check_enabled = True
+    p.obstacle_order = [100 + i for i in range(5)]
+    p.plan()
+    assert p.optimal_trajectory is not None and p.last_plan_stats.n_candidates > 0
