@@ -166,20 +166,21 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------
 # CPU arms
 # ----------------------------------------------------------------------------------------------
-def cpu_port_throughput(w, S, budget_s=12.0, min_reps=2):
+def cpu_port_throughput(w, S, budget_s=12.0, min_reps=2, max_reps=200):
     """Time the C/OpenMP oracle (reference-equivalent CPU path, lazy collision walk like
-    planner.py:329-392) on `S`; returns (cand/s, threads, reps, seconds)."""
+    planner.py:329-392) on `S` with all host threads; returns (cand/s, threads, reps, seconds, last result).
+    Output arrays are allocated once and reused (the reference also reuses its per-candidate arrays)."""
     from oracle import c_oracle
     ref, prm = oracle_inputs(w)
     threads = c_oracle.max_threads()
     Tv = np.unique(S[:, 1])
-    c_oracle.plan(S[:2048], ref, prm, w["preds"], check_all_collisions=False, want_states=True, want_margins=False,
-                  T_values=Tv)                                       # warm-up
+    buf = {}
+    kw = dict(check_all_collisions=False, want_states=True, want_margins=False, T_values=Tv, buffers=buf)
+    out = c_oracle.plan(S, ref, prm, w["preds"], **kw)              # warm-up (threads, pages)
     reps, t_acc = 0, 0.0
-    while reps < min_reps or (t_acc < budget_s and reps < 200):
+    while reps < min_reps or (t_acc < budget_s and reps < max_reps):
         t0 = time.perf_counter()
-        out = c_oracle.plan(S, ref, prm, w["preds"], check_all_collisions=False, want_states=True,
-                            want_margins=False, T_values=Tv)
+        out = c_oracle.plan(S, ref, prm, w["preds"], **kw)
         t_acc += time.perf_counter() - t0
         reps += 1
     return S.shape[0] * reps / t_acc, threads, reps, t_acc, out
@@ -199,11 +200,18 @@ def run_reference_arm(args, w, S):
     """--impl reference: the reference's CPU path on the host cores.  The reference itself (pure
     Python + un-vendored frenetix/commonroad wheels) cannot be installed offline, so this times the
     C/OpenMP port in oracle/ (DESIGN.md section 6)."""
+    from oracle import c_oracle
+    ref, prm = oracle_inputs(w)
+    threads = c_oracle.max_threads()
+    Tv = np.unique(S[:, 1])
+    buf = {}
+    kw = dict(check_all_collisions=False, want_states=True, want_margins=False, T_values=Tv, buffers=buf)
     vals = []
     for i in range(args.warmup + args.steps):
-        thr, threads, reps, secs, _ = cpu_port_throughput(w, S, budget_s=0.0, min_reps=1)
+        t0 = time.perf_counter()
+        c_oracle.plan(S, ref, prm, w["preds"], **kw)
         if i >= args.warmup:
-            vals.append((S.shape[0] / thr))
+            vals.append(time.perf_counter() - t0)
     sec_per_step = float(np.mean(vals))
     value = S.shape[0] / sec_per_step
     line = {

@@ -72,7 +72,8 @@ def pack_predictions(predictions):
 
 def plan(sampling, ref: fo.RefPath, prm: fo.Params, predictions=(), static_obbs=None,
          check_all_collisions=True, collision_check=True, want_states=True, want_margins=True, nthreads=0,
-         T_values=None):
+         T_values=None, buffers=None):
+    """`buffers`: dict reused across calls (timing runs: keeps page faults of fresh arrays out of the loop)."""
     L = lib()
     S = np.ascontiguousarray(sampling, dtype=np.float64)
     n = S.shape[0]
@@ -97,10 +98,15 @@ def plan(sampling, ref: fo.RefPath, prm: fo.Params, predictions=(), static_obbs=
             (ref.ref_pos, ref.ref_theta, ref.ref_curv, ref.ref_curv_d, ref.ref_x, ref.ref_y)]
     obs_pos = None if prm.obstacle_positions is None else np.ascontiguousarray(prm.obstacle_positions, dtype=np.float64)
     sobb = None if static_obbs is None or len(static_obbs) == 0 else np.ascontiguousarray(static_obbs, dtype=np.float64)
-    states = np.zeros((14, n, Nt)) if want_states else None
-    costs = np.zeros((n, max(K, 1))); total = np.zeros(n)
-    flags = np.zeros(n, dtype=np.uint32); tl = np.zeros(n, dtype=np.int32)
-    margins = np.zeros(n) if want_margins else None
+    if buffers is not None and buffers.get("n") == (n, Nt, K):
+        states, costs, total, flags, tl, margins = (buffers[k] for k in ("states", "costs", "total", "flags", "tl", "margins"))
+    else:
+        states = np.zeros((14, n, Nt)) if want_states else None
+        costs = np.zeros((n, max(K, 1))); total = np.zeros(n)
+        flags = np.zeros(n, dtype=np.uint32); tl = np.zeros(n, dtype=np.int32)
+        margins = np.zeros(n) if want_margins else None
+        if buffers is not None:
+            buffers.update(n=(n, Nt, K), states=states, costs=costs, total=total, flags=flags, tl=tl, margins=margins)
     res = OrcResult()
     rc = L.orc_plan(C.byref(P), C.c_int64(n), _p(S), C.c_int(arrs[0].size), *[_p(a) for a in arrs],
                     C.c_int(Tv.size), _p(Tv), _p(Tl, C.c_int32), _p(tp),
