@@ -30,6 +30,27 @@ if ROOT not in sys.path:
 from frenetix_motion_planner_b200 import synthetic as syn  # noqa: E402
 from frenetix_motion_planner_b200.coordinate_system import CoordinateSystem  # noqa: E402
 
+_SAVED_STDOUT = None
+
+
+def quiet_stdout():
+    """stdout carries exactly ONE JSON line: whatever libraries print on fd 1 meanwhile (NCCL banner ...) goes to stderr."""
+    global _SAVED_STDOUT
+    if _SAVED_STDOUT is None:
+        sys.stdout.flush()
+        _SAVED_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    sys.stdout.flush()
+    if _SAVED_STDOUT is not None:
+        os.dup2(_SAVED_STDOUT, 1)
+    print(json.dumps(obj), flush=True)
+    if _SAVED_STDOUT is not None:
+        os.dup2(2, 1)
+
+
 METRIC = "candidate trajectories evaluated/sec per planning step"
 UNIT = "candidates/s"
 
@@ -225,7 +246,7 @@ def run_reference_arm(args, w, S):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def run_config4(args, w, local_rank):
@@ -272,7 +293,7 @@ def run_config4(args, w, local_rank):
         os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
     kmean = float(np.mean(kms))
     ach = rows * B_cand / (kmean * 1e-3) / 1e9
-    print(json.dumps({
+    emit(({
         "metric": METRIC, "value": rows * args.steps / dt, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -320,7 +341,7 @@ def main():
             run_reference_arm(args, w, S)
         return
 
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep stdout to the one JSON line
+    quiet_stdout()
     import torch
     import torch.distributed as dist
     from frenetix_motion_planner_b200 import _capi, hotpath
@@ -371,11 +392,18 @@ def main():
     def step_resident():
         if grid_mode:
             r = h.plan_grid(w["t1"], w["v1"], w["d1"], w["x_cl"], row_first=first, row_count=count)
+            if ex is not None:
+                ex.exchange(r.min_cost, r.argmin, handler=h)
+        elif ex is not None:
+            # plan, all-gather of the 16-byte winner records and their read-back are queued back to back;
+            # the host blocks once
+            h.plan_device_async(S_dev.data_ptr(), count, row_index_base=first)
+            ex.enqueue(h)
+            r = h.plan_wait()
+            ex.finish()
         else:
             r = h.plan_device(S_dev.data_ptr(), count, row_index_base=first)
         launches["n"] += 1 + n_aux
-        if ex is not None:
-            ex.exchange(r.min_cost, r.argmin, handler=h)
         return r
 
     def step_e2e():
@@ -501,7 +529,7 @@ def main():
                 "python_path_1core": py,
                 "selected_row_matches_gpu": (bool(out_cpu["argmin"] + (0 if grid_mode else first) == row_e2e)
                                               if not grid_mode else None)}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

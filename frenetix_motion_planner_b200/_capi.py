@@ -64,7 +64,7 @@ class FrxResult(C.Structure):
 
 EXPORTS = ("frx_abi_version", "frx_create", "frx_destroy", "frx_last_error", "frx_set_reference", "frx_set_params",
            "frx_set_time_tables", "frx_set_predictions", "frx_set_obstacle_positions", "frx_set_static_obbs",
-           "frx_plan", "frx_plan_device", "frx_plan_grid", "frx_plan_batched", "frx_state_pitch", "frx_get_states",
+           "frx_plan", "frx_plan_device", "frx_plan_device_async", "frx_plan_wait", "frx_plan_grid", "frx_plan_batched", "frx_state_pitch", "frx_get_states",
            "frx_get_states_range", "frx_get_costs", "frx_get_flags", "frx_device_pointers", "frx_winner_device_pointer",
            "frx_selftest_fdiv", "frx_set_stream",
            "frx_synchronize")
@@ -100,6 +100,8 @@ def load_library(path: Optional[str] = None):
     lib.frx_set_static_obbs.argtypes = [vp, C.c_int32, dp]
     lib.frx_plan.argtypes = [vp, C.c_int64, dp, C.c_int64, C.POINTER(FrxResult)]
     lib.frx_plan_device.argtypes = [vp, C.c_int64, vp, C.c_int64, C.POINTER(FrxResult)]
+    lib.frx_plan_device_async.argtypes = [vp, C.c_int64, vp, C.c_int64]
+    lib.frx_plan_wait.argtypes = [vp, C.POINTER(FrxResult)]
     lib.frx_plan_grid.argtypes = [vp, C.c_int32, dp, C.c_int32, dp, C.c_int32, dp, dp, C.c_int64, C.c_int64,
                                   C.POINTER(FrxResult)]
     lib.frx_plan_batched.argtypes = [C.c_int32, C.POINTER(vp), C.POINTER(C.c_int64), C.POINTER(dp), C.POINTER(FrxResult)]
@@ -248,6 +250,16 @@ class Handler:
         res = FrxResult()
         self._check(self._lib.frx_plan_device(self._ctx, int(n_rows), C.c_void_p(device_ptr), int(row_index_base), C.byref(res)))
         self.n_rows = int(n_rows)
+        return res
+
+    def plan_device_async(self, device_ptr: int, n_rows: int, row_index_base: int = 0) -> None:
+        """Enqueue only; pair with :meth:`plan_wait`."""
+        self._check(self._lib.frx_plan_device_async(self._ctx, int(n_rows), C.c_void_p(device_ptr), int(row_index_base)))
+        self.n_rows = int(n_rows)
+
+    def plan_wait(self) -> FrxResult:
+        res = FrxResult()
+        self._check(self._lib.frx_plan_wait(self._ctx, C.byref(res)))
         return res
 
     def plan_grid(self, t1, ss1, d1, x_cl, row_first: int = 0, row_count: Optional[int] = None) -> FrxResult:

@@ -73,6 +73,7 @@ struct frx_ctx {
     DevBuf<FrxKernelArgs> batch_args; DevBuf<int> batch_cta;
     HostResult* h_res = nullptr;       // pinned + mapped
     HostResult* d_res = nullptr;       // device address of h_res
+    bool pending = false;              // an asynchronous plan is in flight on `stream`
     bool counters_dirty = true;        // counters must be zeroed before the next launch (first use / after an error)
 
     long long lastN = 0; int lastK = 0; int lastNtp = 0;
@@ -372,10 +373,9 @@ static int fill_result(frx_ctx* ctx, long long N, frx_result* out) {
     return FRX_OK;
 }
 
-static int run_plan(frx_ctx* ctx, long long N, const double* d_sampling, bool grid_mode, int g_nv, int g_nd,
-                    const double* d_t1, const double* d_v1, const double* d_d1, const double* xcl,
-                    long long row_first, long long row_base, frx_result* out) {
-    REQUIRE(out != nullptr, "frx_plan: null result");
+static int enqueue_plan(frx_ctx* ctx, long long N, const double* d_sampling, bool grid_mode, int g_nv, int g_nd,
+                        const double* d_t1, const double* d_v1, const double* d_d1, const double* xcl,
+                        long long row_first, long long row_base) {
     cudaStream_t st = ctx->stream;
     FrxKernelArgs a;
     int grid = 1, nchunk = 1;
@@ -389,14 +389,31 @@ static int run_plan(frx_ctx* ctx, long long N, const double* d_sampling, bool gr
     rc = enqueue_finish(ctx, N, row_base, grid, st);
     if (rc != FRX_OK) return rc;
     CK(cudaEventRecord(ctx->ev1, st));
-    CK(cudaStreamSynchronize(st));
+    ctx->pending = true;
+    return FRX_OK;
+}
+
+static int wait_plan(frx_ctx* ctx, frx_result* out) {
+    REQUIRE(out != nullptr, "frx_plan: null result");
+    REQUIRE(ctx->pending, "frx_plan_wait: no plan in flight");
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->pending = false;
     ctx->counters_dirty = false;         // the last CTA re-armed them
-    rc = fill_result(ctx, N, out);
+    int rc = fill_result(ctx, ctx->lastN, out);
     if (rc != FRX_OK) return rc;
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, ctx->evk0, ctx->evk1)); out->eval_kernel_ms = ms;
     CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1)); out->total_device_ms = ms;
     return FRX_OK;
+}
+
+static int run_plan(frx_ctx* ctx, long long N, const double* d_sampling, bool grid_mode, int g_nv, int g_nd,
+                    const double* d_t1, const double* d_v1, const double* d_d1, const double* xcl,
+                    long long row_first, long long row_base, frx_result* out) {
+    REQUIRE(out != nullptr, "frx_plan: null result");
+    int rc = enqueue_plan(ctx, N, d_sampling, grid_mode, g_nv, g_nd, d_t1, d_v1, d_d1, xcl, row_first, row_base);
+    if (rc != FRX_OK) return rc;
+    return wait_plan(ctx, out);
 }
 
 int frx_plan(frx_ctx* ctx, int64_t N, const double* sampling, int64_t row_index_base, frx_result* out) {
@@ -415,6 +432,20 @@ int frx_plan_device(frx_ctx* ctx, int64_t N, const void* d_sampling, int64_t row
     CK(cudaSetDevice(ctx->device));
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
     return run_plan(ctx, N, (const double*)d_sampling, false, 0, 0, nullptr, nullptr, nullptr, nullptr, 0, row_index_base, out);
+}
+
+int frx_plan_device_async(frx_ctx* ctx, int64_t N, const void* d_sampling, int64_t row_index_base) {
+    if (!ctx) return FRX_ERR_INVALID;
+    REQUIRE(N >= 1 && d_sampling != nullptr, "frx_plan_device_async: empty sampling matrix");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    return enqueue_plan(ctx, N, (const double*)d_sampling, false, 0, 0, nullptr, nullptr, nullptr, nullptr, 0, row_index_base);
+}
+
+int frx_plan_wait(frx_ctx* ctx, frx_result* out) {
+    if (!ctx) return FRX_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    return wait_plan(ctx, out);
 }
 
 int frx_plan_grid(frx_ctx* ctx, int32_t nt, const double* t1, int32_t nv, const double* ss1, int32_t nd,

@@ -60,6 +60,31 @@ class ArgminExchange:
         self._local = None
         self._views = {}
 
+    def enqueue(self, handler) -> None:
+        """nccl only: queue the all-gather of `handler`'s winner record (and the read-back of the gathered
+        records) behind the plan that is in flight on the current stream -- no host synchronisation."""
+        torch, dist = self.torch, self.dist
+        dev = torch.device("cuda", torch.cuda.current_device())
+        if self._gather is None:
+            self._gather = torch.empty(16 * self.world, dtype=torch.uint8, device=dev)
+            self._host = torch.empty(16 * self.world, dtype=torch.uint8).pin_memory()
+        ptr = handler.winner_device_pointer()
+        v = self._views.get(ptr)
+        if v is None:
+            v = self._views[ptr] = torch.as_tensor(_DevView(ptr, 16), device=dev)
+        dist.all_gather_into_tensor(self._gather, v, group=self.group)
+        self._host.copy_(self._gather, non_blocking=True)
+
+    def finish(self) -> Tuple[float, int, int]:
+        """After the stream has been synchronised (frx_plan_wait does): reduce the gathered records."""
+        raw = self._host.numpy().tobytes()
+        recs = [struct.unpack_from("<dq", raw, 16 * r) for r in range(self.world)]
+        costs = np.array([c for c, _ in recs])
+        rows = np.array([r for _, r in recs], dtype=np.int64)
+        c, r = reduce_winners(costs, rows)
+        owner = int(np.nonzero(rows == r)[0][0]) if r >= 0 else -1
+        return c, r, owner
+
     def exchange(self, min_cost: float, global_row: int, handler=None) -> Tuple[float, int, int]:
         """-> (global min cost, global row, owner rank).  `handler`: the _capi.Handler whose winner record
         should be sent straight from HBM (nccl only)."""

@@ -148,6 +148,11 @@ int frx_plan(frx_ctx* ctx, int64_t N, const double* sampling, int64_t row_index_
 /* same, sampling already in device memory (pointer from cudaMalloc / torch) */
 int frx_plan_device(frx_ctx* ctx, int64_t N, const void* d_sampling, int64_t row_index_base,
                     frx_result* out);
+/* Asynchronous form: enqueue the plan on the context's stream and return; frx_plan_wait synchronises and
+ * fills the result.  Lets a caller queue the multi-GPU exchange (or its own kernels) behind the plan
+ * before blocking once. */
+int frx_plan_device_async(frx_ctx* ctx, int64_t N, const void* d_sampling, int64_t row_index_base);
+int frx_plan_wait(frx_ctx* ctx, frx_result* out);
 /* rows generated on device in itertools.product order (t1 slowest, then ss1, then d1);
  * x_cl = s0,ss0,sss0,d0,dd0,ddd0; evaluates global rows [row_first, row_first + row_count) */
 int frx_plan_grid(frx_ctx* ctx, int32_t nt, const double* t1, int32_t nv, const double* ss1,
