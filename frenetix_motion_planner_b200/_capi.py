@@ -66,7 +66,7 @@ EXPORTS = ("frx_abi_version", "frx_create", "frx_destroy", "frx_last_error", "fr
            "frx_set_time_tables", "frx_set_predictions", "frx_set_obstacle_positions", "frx_set_static_obbs",
            "frx_plan", "frx_plan_device", "frx_plan_device_async", "frx_plan_wait", "frx_plan_grid", "frx_plan_batched", "frx_state_pitch", "frx_get_states",
            "frx_get_states_range", "frx_get_costs", "frx_get_flags", "frx_device_pointers", "frx_winner_device_pointer",
-           "frx_selftest_fdiv", "frx_set_stream",
+           "frx_selftest_fdiv", "frx_selftest_divc", "frx_set_stream",
            "frx_synchronize")
 
 _lib = None
@@ -113,6 +113,7 @@ def load_library(path: Optional[str] = None):
     lib.frx_device_pointers.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     lib.frx_winner_device_pointer.argtypes = [vp, C.POINTER(vp)]
     lib.frx_selftest_fdiv.argtypes = [vp, C.c_int64, dp, dp, dp, dp]
+    lib.frx_selftest_divc.argtypes = [vp, C.c_int64, dp, C.c_double, dp, dp]
     lib.frx_set_stream.argtypes = [vp, vp]
     lib.frx_synchronize.argtypes = [vp]
     for name in EXPORTS:
@@ -330,6 +331,12 @@ class Handler:
         a, b = _f64(a), _f64(b)
         q1, q2 = np.empty_like(a), np.empty_like(a)
         self._check(self._lib.frx_selftest_fdiv(self._ctx, a.size, _dptr(a), _dptr(b), _dptr(q1), _dptr(q2)))
+        return q1, q2
+
+    def selftest_divc(self, a, b: float):
+        a = _f64(a)
+        q1, q2 = np.empty_like(a), np.empty_like(a)
+        self._check(self._lib.frx_selftest_divc(self._ctx, a.size, _dptr(a), float(b), _dptr(q1), _dptr(q2)))
         return q1, q2
 
     def winner_device_pointer(self) -> int:

@@ -27,6 +27,7 @@ void frx_launch_gather(const double* states, long long N, int Ntp, const long lo
                        uint32_t mask, double* out, cudaStream_t st);
 
 void frx_launch_selftest_fdiv(long long n, const double* a, const double* b, double* q1, double* q2, cudaStream_t st);
+void frx_launch_selftest_divc(long long n, const double* a, double b, double* q1, double* q2, cudaStream_t st);
 
 namespace {
 
@@ -312,6 +313,7 @@ static int prepare_plan(frx_ctx* ctx, long long N, const double* d_sampling, boo
     FrxKernelArgs a;
     memset(&a, 0, sizeof(a));
     a.dt = p.dt; a.a_max = p.a_max; a.v_switch = p.v_switch; a.kappa_max = ctx->kappa_max; a.wb_rear = p.wb_rear_axle;
+    a.inv_dt = 1.0 / p.dt; a.inv_Nt = 1.0 / (double)Nt;
     a.half_len = p.length / 2; a.half_wid = p.width / 2; a.x0_orientation = p.x0_orientation; a.v_des = p.desired_velocity;
     for (int k = 0; k < K; ++k) { a.w[k] = p.cost_weights[k]; a.cost_ids[k] = p.cost_ids[k]; }
     a.n_costs = K; a.Nt = Nt; a.Ntp = Ntp; a.low = p.low_vel_mode; a.draw = p.draw_traj_set; a.debug = p.kinematic_debug;
@@ -604,6 +606,22 @@ int frx_selftest_fdiv(frx_ctx* ctx, int64_t n, const double* a, const double* b,
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(q_fdiv, buf.p + 2 * n, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(q_ieee, buf.p + 3 * n, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    buf.release();
+    return FRX_OK;
+}
+
+int frx_selftest_divc(frx_ctx* ctx, int64_t n, const double* a, double b, double* q_divc, double* q_ieee) {
+    if (!ctx) return FRX_ERR_INVALID;
+    REQUIRE(n >= 1 && a && q_divc && q_ieee, "frx_selftest_divc: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    DevBuf<double> buf;
+    CK(buf.reserve((size_t)n * 3));
+    CK(cudaMemcpyAsync(buf.p, a, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+    frx_launch_selftest_divc(n, buf.p, b, buf.p + n, buf.p + 2 * n, ctx->stream);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(q_divc, buf.p + n, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(q_ieee, buf.p + 2 * n, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     buf.release();
     return FRX_OK;

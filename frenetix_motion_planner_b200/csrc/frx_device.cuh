@@ -3,10 +3,15 @@
 #include <stdint.h>
 #include "frx.h"
 
+#ifndef FRX_WARPS_PER_CTA
 #define FRX_WARPS_PER_CTA 4
+#endif
 #define FRX_THREADS (FRX_WARPS_PER_CTA * 32)
 #ifndef FRX_MIN_CTAS
 #define FRX_MIN_CTAS 5   // resident CTAs per SM the 32-step eval kernel is compiled for (register cap 102)
+#endif
+#ifndef FRX_MIN_CTAS2    // ... and the 64-step instance (two chunks per candidate, more live registers)
+#define FRX_MIN_CTAS2 ((FRX_MIN_CTAS > 3) ? (FRX_MIN_CTAS - 2) : 1)
 #endif
 #define FRX_MAX_T_VALUES 128
 #ifndef FRX_CHUNK_ROWS
@@ -49,6 +54,7 @@ struct FrxHostResult {
 struct FrxKernelArgs {
     // ---- scalars (frx_params, pre-digested on the host)
     double dt, a_max, v_switch, kappa_max, wb_rear, half_len, half_wid, x0_orientation, v_des;
+    double inv_dt, inv_Nt;  // correctly rounded 1/dt and 1/Nt (host), for ddivc
     double w[FRX_MAX_COSTS];
     int cost_ids[FRX_MAX_COSTS];
     int n_costs;

@@ -180,6 +180,9 @@ int frx_device_pointers(frx_ctx* ctx, void** states, void** costs, void** total,
 int frx_winner_device_pointer(frx_ctx* ctx, void** winner);
 /* diagnostics: the kernels' slow-path-free fp64 division next to IEEE division (tests only) */
 int frx_selftest_fdiv(frx_ctx* ctx, int64_t n, const double* a, const double* b, double* q_fdiv, double* q_ieee);
+/* diagnostics: the kernels' division by a plan constant b (dt, 100000, Nt; reciprocal precomputed on the host)
+ * next to IEEE division (tests only) */
+int frx_selftest_divc(frx_ctx* ctx, int64_t n, const double* a, double b, double* q_divc, double* q_ieee);
 /* use an externally created stream (e.g. torch's current stream); 0 restores the private stream */
 int frx_set_stream(frx_ctx* ctx, void* cuda_stream);
 int frx_synchronize(frx_ctx* ctx);

@@ -55,3 +55,19 @@ def test_fdiv_is_ieee_division():
         ref = a / b
     same_host = (q1 == ref) | (np.isnan(q1) & np.isnan(ref))
     assert same_host.all()
+
+
+@pytest.mark.gpu
+def test_division_by_plan_constants_is_ieee_exact():
+    """ddivc(a, b, 1/b) (kernels: yaw rate / dt, rint(.)/100000, sum / Nt) equals IEEE a / b bit for bit."""
+    from frenetix_motion_planner_b200 import _capi
+    h = _capi.Handler(0)
+    rng = np.random.default_rng(7)
+    n = 1_000_000
+    a = rng.normal(0, 1, n) * 10.0 ** rng.integers(-12, 12, n)
+    a[:1000] = np.rint(rng.normal(0, 1e5, 1000))
+    a[1000:1100] = 0.0
+    for b in (0.1, 0.2, 0.05, 100000.0, 31.0, 51.0, 21.0, 61.0):
+        q1, q2 = h.selftest_divc(a, b)
+        assert (q1 == q2).all(), f"b={b}: {(q1 != q2).sum()} mismatches"
+        assert (q1 == a / b).all()
