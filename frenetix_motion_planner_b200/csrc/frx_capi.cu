@@ -23,8 +23,9 @@ void frx_launch_static_prep(int B, const double* obb, double* out, cudaStream_t 
 void frx_launch_argmin(const FrxBest* bb, int nblocks, long long row_base, FrxBest* out, cudaStream_t st);
 void frx_launch_collision_counter(long long N, long long row_base, const double* total, const uint32_t* flags,
                                   const FrxBest* winner, unsigned long long* counters, int grid, cudaStream_t st);
-void frx_launch_gather(const double* states, long long N, int Ntp, const long long* idx, long long n_idx,
-                       uint32_t mask, double* out, cudaStream_t st);
+void frx_launch_gather(const double* states, long long Np, int Nt, int Ntp, const long long* idx, long long first,
+                       long long n_idx, uint32_t mask, double* out, cudaStream_t st);
+void frx_features(const FrxKernelArgs& a, bool* obs, bool* xcost);
 
 void frx_launch_selftest_fdiv(long long n, const double* a, const double* b, double* q1, double* q2, cudaStream_t st);
 void frx_launch_selftest_divc(long long n, const double* a, double b, double* q1, double* q2, cudaStream_t st);
@@ -77,7 +78,8 @@ struct frx_ctx {
     bool pending = false;              // an asynchronous plan is in flight on `stream`
     bool counters_dirty = true;        // counters must be zeroed before the next launch (first use / after an error)
 
-    long long lastN = 0; int lastK = 0; int lastNtp = 0;
+    long long lastN = 0, lastNp = 0; int lastK = 0, lastNt = 0, lastNtp = 0;
+    bool last_all_fields = false;     // the last plan materialised all 14 state planes
     int occ_Mpad = -1, occ_nchunk = -1, occ_blocks = 1;
 };
 
@@ -286,7 +288,11 @@ static int prepare_plan(frx_ctx* ctx, long long N, const double* d_sampling, boo
             "frx_plan: frx_set_params, frx_set_reference and frx_set_time_tables must be called first");
     const frx_params& p = ctx->prm;
     const int Nt = p.N + 1, Ntp = pitch_for(Nt), nchunk = nchunk_for(Nt), K = p.n_costs;
-    if (p.store_states) CK(ctx->states.reserve((size_t)FRX_NUM_FIELDS * N * Ntp));
+    const long long Np = (N + 31) & ~31LL;         // candidates per (field, step) plane, padded to whole tiles
+    // without store_states only the x, y, theta planes exist, and only when the obstacle pass re-reads them
+    const bool need_xyt = (ctx->O > 0 || ctx->B > 0 || ctx->n_obs_pos > 0);
+    if (p.store_states) CK(ctx->states.reserve((size_t)FRX_NUM_FIELDS * Nt * Np));
+    else if (need_xyt) CK(ctx->states.reserve((size_t)3 * Nt * Np));
     CK(ctx->costs.reserve((size_t)N * (K > 0 ? K : 1))); CK(ctx->total.reserve(N)); CK(ctx->flags.reserve(N));
     CK(ctx->traj_len.reserve(N));
     if (ctx->occ_Mpad != ctx->Mpad || ctx->occ_nchunk != nchunk) {
@@ -304,7 +310,8 @@ static int prepare_plan(frx_ctx* ctx, long long N, const double* d_sampling, boo
         CK(cudaGetLastError());
         ctx->Tp = Tp;
     }
-    long long want = (N + FRX_WARPS_PER_CTA - 1) / FRX_WARPS_PER_CTA;   // at least one row per warp
+    const long long n_tiles = (N + 31) / 32;       // one warp per tile of 32 rows
+    long long want = (n_tiles + FRX_WARPS_PER_CTA - 1) / FRX_WARPS_PER_CTA;
     long long full = (max_grid > 0) ? max_grid : (long long)ctx->sm_count * ctx->occ_blocks;
     int grid = (int)(want < full ? want : full);
     if (grid < 1) grid = 1;
@@ -327,6 +334,7 @@ static int prepare_plan(frx_ctx* ctx, long long N, const double* d_sampling, boo
     if (xcl) for (int k = 0; k < 6; ++k) a.xcl[k] = xcl[k];
     a.row_first = row_first; a.row_base = row_base; a.N = N;
     a.states = ctx->states.p; a.costs = ctx->costs.p; a.total = ctx->total.p; a.flags = ctx->flags.p;
+    a.Np = Np; a.keep_xyt = (!p.store_states && need_xyt) ? 1 : 0;
     a.traj_len = ctx->traj_len.p; a.blockbest = ctx->blockbest.p; a.counters = ctx->counters.p;
     a.winner = ctx->winner.p; a.host_res = ctx->d_res; a.n_cta = grid;
     if (ctx->counters_dirty) {
@@ -334,7 +342,8 @@ static int prepare_plan(frx_ctx* ctx, long long N, const double* d_sampling, boo
         ctx->counters_dirty = false;
     }
     *a_out = a; *grid_out = grid; *nchunk_out = nchunk;
-    ctx->lastN = N; ctx->lastK = K; ctx->lastNtp = Ntp;
+    ctx->lastN = N; ctx->lastNp = Np; ctx->lastK = K; ctx->lastNt = Nt; ctx->lastNtp = Ntp;
+    ctx->last_all_fields = p.store_states != 0;
     return FRX_OK;
 }
 
@@ -539,7 +548,7 @@ int32_t frx_state_pitch(const frx_ctx* ctx) { return ctx ? ctx->lastNtp : 0; }
 
 int frx_get_states(frx_ctx* ctx, int64_t n_idx, const int64_t* idx, uint32_t field_mask, double* out) {
     if (!ctx) return FRX_ERR_INVALID;
-    REQUIRE(ctx->lastN > 0 && ctx->prm.store_states, "frx_get_states: no materialised states (store_states = 0 or no plan yet)");
+    REQUIRE(ctx->lastN > 0 && ctx->last_all_fields, "frx_get_states: no materialised states (store_states = 0 or no plan yet)");
     REQUIRE(n_idx >= 1 && idx && out && field_mask && field_mask < (1u << FRX_NUM_FIELDS), "frx_get_states: bad arguments");
     for (int64_t k = 0; k < n_idx; ++k) REQUIRE(idx[k] >= 0 && idx[k] < ctx->lastN, "frx_get_states: row index out of range");
     CK(cudaSetDevice(ctx->device));
@@ -547,7 +556,8 @@ int frx_get_states(frx_ctx* ctx, int64_t n_idx, const int64_t* idx, uint32_t fie
     const size_t n_out = (size_t)nf * n_idx * ctx->lastNtp;
     CK(ctx->gidx.reserve(n_idx)); CK(ctx->gout.reserve(n_out));
     CK(cudaMemcpyAsync(ctx->gidx.p, idx, sizeof(long long) * n_idx, cudaMemcpyHostToDevice, ctx->stream));
-    frx_launch_gather(ctx->states.p, ctx->lastN, ctx->lastNtp, ctx->gidx.p, n_idx, field_mask, ctx->gout.p, ctx->stream);
+    frx_launch_gather(ctx->states.p, ctx->lastNp, ctx->lastNt, ctx->lastNtp, ctx->gidx.p, 0, n_idx, field_mask, ctx->gout.p,
+                      ctx->stream);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(out, ctx->gout.p, n_out * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -556,17 +566,29 @@ int frx_get_states(frx_ctx* ctx, int64_t n_idx, const int64_t* idx, uint32_t fie
 
 int frx_get_states_range(frx_ctx* ctx, int64_t first, int64_t count, uint32_t field_mask, double* out) {
     if (!ctx) return FRX_ERR_INVALID;
-    REQUIRE(ctx->lastN > 0 && ctx->prm.store_states, "frx_get_states_range: no materialised states");
+    REQUIRE(ctx->lastN > 0 && ctx->last_all_fields, "frx_get_states_range: no materialised states");
     REQUIRE(first >= 0 && count >= 1 && first + count <= ctx->lastN && out && field_mask && field_mask < (1u << FRX_NUM_FIELDS),
             "frx_get_states_range: bad arguments");
     CK(cudaSetDevice(ctx->device));
-    const size_t rowb = (size_t)ctx->lastNtp * sizeof(double);
-    size_t fo = 0;
-    for (int f = 0; f < FRX_NUM_FIELDS; ++f) {
-        if (!(field_mask & (1u << f))) continue;
-        CK(cudaMemcpyAsync((char*)out + fo * count * rowb, ctx->states.p + ((size_t)f * ctx->lastN + first) * ctx->lastNtp,
-                           (size_t)count * rowb, cudaMemcpyDeviceToHost, ctx->stream));
-        ++fo;
+    // the tensor is [field][step][candidate]; the caller gets [field][candidate][pitch]: transpose on the device in
+    // slabs of bounded size, then copy out
+    const int nf = __builtin_popcount(field_mask);
+    const size_t per_row = (size_t)ctx->lastNtp;
+    long long slab = (long long)((size_t)(64u << 20) / (per_row * sizeof(double)));     // <= 64 Mi doubles... per field
+    if (slab < 1) slab = 1;
+    if (slab > count) slab = count;
+    CK(ctx->gout.reserve((size_t)slab * per_row));
+    uint32_t m = field_mask;
+    for (int fo = 0; fo < nf; ++fo) {
+        const int f = __builtin_ctz(m); m &= m - 1;
+        for (long long done = 0; done < count; done += slab) {
+            const long long n = (count - done < slab) ? (count - done) : slab;
+            frx_launch_gather(ctx->states.p, ctx->lastNp, ctx->lastNt, ctx->lastNtp, nullptr, first + done, n, 1u << f, ctx->gout.p,
+                              ctx->stream);
+            CK(cudaGetLastError());
+            CK(cudaMemcpyAsync(out + ((size_t)fo * count + done) * per_row, ctx->gout.p, (size_t)n * per_row * sizeof(double),
+                               cudaMemcpyDeviceToHost, ctx->stream));
+        }
     }
     CK(cudaStreamSynchronize(ctx->stream));
     return FRX_OK;

@@ -8,7 +8,7 @@
 #endif
 #define FRX_THREADS (FRX_WARPS_PER_CTA * 32)
 #ifndef FRX_MIN_CTAS
-#define FRX_MIN_CTAS 5   // resident CTAs per SM the 32-step eval kernel is compiled for (register cap 102)
+#define FRX_MIN_CTAS 3   // resident CTAs per SM the eval kernel is compiled for (register cap 168)
 #endif
 #ifndef FRX_MIN_CTAS2    // ... and the 64-step instance (two chunks per candidate, more live registers)
 #define FRX_MIN_CTAS2 ((FRX_MIN_CTAS > 3) ? (FRX_MIN_CTAS - 2) : 1)
@@ -86,7 +86,9 @@ struct FrxKernelArgs {
     long long row_base;     // added to the local index when reporting argmin
     long long N;
     // ---- outputs
-    double* states;         // [14][N][Ntp]
+    double* states;         // [14][Nt][Np]: field, step, candidate (candidate fastest, Np = N rounded up to 32)
+    long long Np;
+    int keep_xyt;           // store_states == 0 but the obstacle pass needs the x, y, theta planes
     double* costs;          // [N][n_costs]
     double* total;          // [N]
     uint32_t* flags;        // [N]

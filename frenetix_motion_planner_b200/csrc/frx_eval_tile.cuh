@@ -1,0 +1,750 @@
+// frx_eval_tile.cuh -- the eval kernel body: ONE THREAD PER CANDIDATE TRAJECTORY, one warp per tile of 32
+// consecutive sampling rows (included by frx_kernels.cu, which provides the arithmetic helpers).
+//
+//   * lane = candidate: the polynomial coefficient solve, the per-candidate bookkeeping and the cost assembly are
+//     per-thread scalar code (useful work in all 32 lanes), the time-step loop runs sequentially in each thread --
+//     time-coupled quantities (yaw rate, curvature rate, stand-still heading carry) are plain registers, no
+//     shuffles, ballots or warp-synchronous code inside the loop, so lanes may diverge freely;
+//   * the state tensor is laid out [field][step][candidate]: at every step the 32 lanes of a warp write 32
+//     consecutive candidates of one field = one fully coalesced 256-byte store;
+//   * everything that depends on the longitudinal motion s(t) only (quartic, samples, reference segment, lambda,
+//     interpolated heading/curvature, foot point, normal, time-power row) is shared by all candidates with the same
+//     (t1, s0, ss0, sss0, ss1): the warp computes it cooperatively ONCE per key (lane = time step, the reference
+//     tables in shared memory staged by a TMA bulk copy) into a per-warp shared-memory memo of two slots; rows of a
+//     sampling matrix come as a cartesian product with d1 fastest, so a tile spans one or two keys (tiles with more
+//     are processed in several passes of two keys each -- correct for ANY matrix, fast for cartesian ones);
+//   * obstacle data (prediction cost, collision sweep) is indexed by the step only -> warp-uniform loads;
+//     the second pass over the steps runs only for the lanes that need it and re-reads x, y, theta of the candidate
+//     from the state tensor (coalesced, L2).
+//
+// Arithmetic follows reactive_planner.py:274-577 of the reference op for op (comments next to each block).
+#pragma once
+
+enum { M_S = 0, M_SD, M_SDD, M_INTERP, M_KR, M_KRD, M_PX, M_PY, M_SN, M_CS, M_T1, M_T2, M_T3, M_T4, M_T5, M_FIELDS };
+
+struct FrxMemoHdr {        // one per memo slot (shared memory)
+    double key[5];         // t1, s0, ss0, sss0, ss1 the slot was filled for
+    double s_first, jerk_lon, goal;
+    int traj_len, first_none, bits, valid;   // bits: 1 any s_d < -eps, 2 any |s_dd| > a_max, 4 duration not registered
+};
+
+#define FRX_MEMO_SLOTS 2
+
+__host__ __device__ inline size_t frx_tile_smem_bytes(int Mpad, int tpitch) {
+    return (size_t)(6 * Mpad + FRX_MAX_T_VALUES + FRX_WARPS_PER_CTA * FRX_MEMO_SLOTS * M_FIELDS * tpitch) * sizeof(double) +
+           FRX_WARPS_PER_CTA * FRX_MEMO_SLOTS * sizeof(FrxMemoHdr) + 16 + FRX_WARPS_PER_CTA * sizeof(FrxBest);
+}
+
+// Simpson-rule accumulator (scipy simps, dx = dt; partial_cost_functions.py:24-46, :141-151, :189-196), fed one
+// sample at a time: `part` is the plain composite sum over the first nb samples, `corr` the last-interval correction
+// scipy applies when the number of samples is even.
+struct FrxSimpson {
+    double part, corr;
+    __device__ __forceinline__ void add(int jx, int n, int nb, double yv, double alpha, double beta, double eta) {
+        if (jx >= 0 && jx < n) {
+            if (jx < nb) {
+                double wgt = (jx == 0 || jx == nb - 1) ? 1.0 : ((jx & 1) ? 4.0 : 2.0);
+                part += wgt * yv;
+            }
+            if (!(n & 1) && n > 2) {
+                if (jx == n - 1) corr += alpha * yv;
+                else if (jx == n - 2) corr += beta * yv;
+                else if (jx == n - 3) corr -= eta * yv;
+            }
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// memo fill: warp-cooperative, lane = time step (chunks of 32).  reactive_planner.py:296-322, :350-355, :415-420,
+// :457-460, :536-547; polynomial_trajectory.py:452-488 (quartic, closed form)
+// ------------------------------------------------------------------------------------------------------------
+__device__ __noinline__ void frx_memo_fill(const FrxKernelArgs& A, const double* __restrict__ s_ref, const double* __restrict__ s_Ttab,
+                                           double* __restrict__ mt, FrxMemoHdr* __restrict__ hdr, const double T, const double s0,
+                                           const double ss0, const double sss0, const double ss1) {
+    const int lane = threadIdx.x & 31;
+    const int Mpad = A.Mpad, M = A.M, Nt = A.Nt, TP = A.tpitch;
+    const double* __restrict__ rp = s_ref;
+    const double* __restrict__ rth = s_ref + Mpad;
+    const double* __restrict__ rc = s_ref + 2 * Mpad;
+    const double* __restrict__ rcd = s_ref + 3 * Mpad;
+    const double* __restrict__ rx = s_ref + 4 * Mpad;
+    const double* __restrict__ ry = s_ref + 5 * Mpad;
+    const double dT = A.dt;
+    const double pos_first = rp[0], pos_last = rp[M - 1];
+    const double inv_step = (double)(M - 1) / (pos_last - pos_first);
+    __syncwarp();
+    if (lane == 0) {
+        hdr->key[0] = T; hdr->key[1] = s0; hdr->key[2] = ss0; hdr->key[3] = sss0; hdr->key[4] = ss1;
+        hdr->valid = 1;
+    }
+    // ---------------- time table of this duration (reactive_planner.py:296-303)
+    int tix = -1;
+    for (int b0 = 0; b0 < A.nT; b0 += 32) {
+        unsigned m = __ballot_sync(FULL, (b0 + lane < A.nT) && (s_Ttab[b0 + lane] == T));
+        if (m) { tix = b0 + __ffs(m) - 1; break; }
+    }
+    if (tix < 0) {   // the host did not register this duration: the rows of this key are reported dead
+        if (lane == 0) { hdr->bits = 4; hdr->traj_len = 0; hdr->first_none = 0; hdr->s_first = hdr->jerk_lon = hdr->goal = 0.0; }
+        __syncwarp();
+        return;
+    }
+    const int traj_len = __ldg(A.Tlen + tix);
+    const double* __restrict__ tp = A.tpow + (size_t)tix * 5 * TP;
+    Poly L;
+    {
+        double T2 = T * T, T3 = T2 * T;
+        double b0 = (ss1 - ss0) - sss0 * T;
+        double b1 = -sss0;
+        L.c0 = s0; L.c1 = ss0; L.c2 = sss0 * 0.5;   // == sss0 / 2.0 exactly
+        L.c3 = ddivf(3 * b0 - T * b1, 3 * T2);
+        L.c4 = ddivf(T * b1 - 2 * b0, 4 * T3);
+        L.c5 = 0.0;
+    }
+    const int il = traj_len - 1;
+    double s_last = 0.0, sd_last = 0.0, s_inc = 0.0;
+    const double s_first = poly_pos(L, __ldg(tp), __ldg(tp + TP), __ldg(tp + 2 * TP), __ldg(tp + 3 * TP), __ldg(tp + 4 * TP));
+    if (traj_len < Nt) {   // values of the last polynomial sample feed the extension of every later step
+        double tl = __ldg(tp + il), tl2 = __ldg(tp + TP + il), tl3 = __ldg(tp + 2 * TP + il), tl4 = __ldg(tp + 3 * TP + il),
+               tl5 = __ldg(tp + 4 * TP + il);
+        s_last = poly_pos(L, tl, tl2, tl3, tl4, tl5);
+        sd_last = poly_vel(L, tl, tl2, tl3, tl4);
+        s_inc = dT * sd_last;
+    }
+    bool any_neg = false, any_acc = false;
+    int first_none = Nt;
+    for (int c0 = 0; c0 < TP; c0 += 32) {
+        const int i = c0 + lane;
+        const bool act = i < Nt;
+        double vs = 0, vsd = 0, vsdd = 0;
+        {
+            double t = __ldg(tp + i), t2 = __ldg(tp + TP + i), t3 = __ldg(tp + 2 * TP + i), t4 = __ldg(tp + 3 * TP + i),
+                   t5 = __ldg(tp + 4 * TP + i);
+            mt[M_T1 * TP + i] = t; mt[M_T2 * TP + i] = t2; mt[M_T3 * TP + i] = t3; mt[M_T4 * TP + i] = t4; mt[M_T5 * TP + i] = t5;
+            if (i < traj_len) {
+                vs = poly_pos(L, t, t2, t3, t4, t5);
+                vsd = poly_vel(L, t, t2, t3, t4);
+                vsdd = poly_acc(L, t, t2, t3);
+            }
+        }
+        if (i >= traj_len && act) {
+            vs = s_last;                        // s[ext] = s[ext-1] + dt * s_velocity[traj_len-1]
+            for (int k = il; k < i; ++k) vs += s_inc;
+            vsd = sd_last; vsdd = 0.0;
+        }
+        any_neg |= __any_sync(FULL, act && (vsd < -FRX_EPS));
+        any_acc |= __any_sync(FULL, act && (fabs(vsdd) > A.a_max));
+        if (fabs(vsd) < FRX_EPS) vsd = 0.0;     // :355
+        // :415-420 segment lookup (python negative-index wrap reproduced), :457-460 curvature
+        int j = first_greater(rp, M, vs, pos_first, inv_step);
+        int ia = (j == 0) ? (M - 1) : (j - 1);
+        double pa = rp[ia], pb = rp[j];
+        double lam = ddivf(vs - pa, pb - pa);
+        double tha = rth[ia], thb = rth[j];
+        double interp = make_valid_orientation(ddivf((thb - tha) * (vs - pa), pb - pa) + tha);
+        double k_r = (rc[j] - rc[ia]) * lam + rc[ia];
+        double k_r_d = (rcd[j] - rcd[ia]) * lam + rcd[ia];
+        // :536-547 foot point and normal of the Cartesian conversion (library definition of CCosy)
+        bool none = !(vs >= pos_first) || !(vs < pos_last);
+        unsigned nm = __ballot_sync(FULL, none && act);
+        if (nm && first_none == Nt) first_none = c0 + __ffs(nm) - 1;
+        double px = (1.0 - lam) * rx[ia] + lam * rx[j];
+        double py = (1.0 - lam) * ry[ia] + lam * ry[j];
+        double thr = tha + lam * (thb - tha);
+        double sn, cs;
+        sincos(thr, &sn, &cs);
+        mt[M_S * TP + i] = vs; mt[M_SD * TP + i] = vsd; mt[M_SDD * TP + i] = vsdd;
+        mt[M_INTERP * TP + i] = interp;
+        mt[M_KR * TP + i] = k_r; mt[M_KRD * TP + i] = k_r_d;
+        mt[M_PX * TP + i] = px; mt[M_PY * TP + i] = py;
+        mt[M_SN * TP + i] = sn; mt[M_CS * TP + i] = cs;
+    }
+    if (lane == 0) {
+        hdr->traj_len = traj_len;
+        hdr->first_none = first_none;
+        hdr->bits = (any_neg ? 1 : 0) | (any_acc ? 2 : 0);
+        hdr->s_first = s_first;
+        hdr->jerk_lon = sq_jerk_integral(L, dT);
+        // reactive_planner.py:161-166 (evaluate_state_at_tau at tau = delta_tau), used in low-velocity mode
+        double t2 = T * T, t3 = t2 * T, t4 = t2 * t2, t5 = t3 * t2;
+        hdr->goal = poly_pos(L, T, t2, t3, t4, t5) - s0;
+    }
+    __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// one candidate, one thread
+// ------------------------------------------------------------------------------------------------------------
+struct FrxLaneOut {
+    unsigned ev;         // event bits (CNT_* order) of this candidate
+    double total;
+    bool winner_ok;      // candidate && !collide && !boundary
+    bool t_missing;
+};
+
+template <bool OBS, bool XCOST>
+__device__ __forceinline__ FrxLaneOut frx_candidate(const FrxKernelArgs& A, const unsigned cost_mask, const long long r,
+                                                    const double T, const double d0, const double dd0, const double ddd0,
+                                                    const double d1, const double dd1, const double ddd1,
+                                                    const double* __restrict__ mt, const FrxMemoHdr* __restrict__ H) {
+    FrxLaneOut out;
+    out.ev = 0; out.total = 0.0; out.winner_ok = false; out.t_missing = false;
+    const int Nt = A.Nt, TP = A.tpitch;
+    const long long Np = A.Np;
+    const double dT = A.dt;
+    const bool low = A.low != 0, draw = A.draw != 0, debug = A.debug != 0;
+    const bool brk = !draw && !debug;
+    const int hbits = H->bits;
+    if (hbits & 4) {
+        A.flags[r] = 0u; A.total[r] = 0.0; A.traj_len[r] = 0;
+        out.t_missing = true;
+        return out;
+    }
+    const int traj_len = H->traj_len;
+    const int il = traj_len - 1;
+    const bool any_neg = (hbits & 1) != 0, any_acc = (hbits & 2) != 0;
+    const double s_first = H->s_first;
+
+    // ---------------- lateral quintic (polynomial_trajectory.py:293-343; closed form)
+    Poly Q;
+    {
+        double tau = T;
+        if (low) { const double goal = H->goal; tau = (goal <= 0) ? T : goal; }
+        double u2 = tau * tau, u3 = u2 * tau, u4 = u2 * u2, u5 = u4 * tau;
+        double b0 = ((d1 - d0) - dd0 * tau) - (.5 * ddd0) * u2;
+        double b1 = (dd1 - dd0) - ddd0 * tau;
+        double b2 = ddd1 - ddd0;
+        Q.c0 = d0; Q.c1 = dd0; Q.c2 = .5 * ddd0;
+        Q.c3 = ddivf((10 * b0 - (4 * b1) * tau) + (0.5 * b2) * u2, u3);
+        Q.c4 = ddivf((-15 * b0 + (7 * b1) * tau) - b2 * u2, u4);
+        Q.c5 = ddivf((6 * b0 - (3 * b1) * tau) + (0.5 * b2) * u2, u5);
+    }
+    double d_last = 0.0;
+    if (traj_len < Nt) {
+        if (!low) {
+            d_last = poly_pos(Q, mt[M_T1 * TP + il], mt[M_T2 * TP + il], mt[M_T3 * TP + il], mt[M_T4 * TP + il], mt[M_T5 * TP + il]);
+        } else {
+            double q1 = mt[M_S * TP + il] - s_first, q2 = q1 * q1, q3 = q2 * q1, q4 = q2 * q2, q5 = q4 * q1;
+            d_last = poly_pos(Q, q1, q2, q3, q4, q5);
+        }
+    }
+
+    // ---------------- validity / pre-filter bookkeeping (:350-386)
+    bool valid = !any_neg;
+    bool feasible = true;
+    uint32_t reasons = 0;
+    bool in_list = true, stored = true;
+    if (any_neg) {
+        reasons |= FRX_FLAG_REASON(10);
+        if (brk) { in_list = false; stored = false; }
+    }
+    if (in_list && !draw) {
+        if (any_acc) { feasible = false; reasons |= FRX_FLAG_REASON(1); stored = false; }
+        else if (any_neg) { feasible = false; reasons |= FRX_FLAG_REASON(2); stored = false; }
+    }
+    const bool evaluate = in_list && stored;    // reaches the per-step loop of :389
+
+    // ---------------- the time-step loop: lateral samples (:325-346), back-projection + gates (:389-533), x/y
+    //                  (:536-547), running cost sums, 14 coalesced stores per step
+    uint32_t gate_or = 0;
+    bool gate_hit = false;
+    const int first_none = H->first_none;
+    const bool seen_none = evaluate && (first_none < Nt);
+    double th_prev = A.x0_orientation;   // theta_gl[i-1]
+    double ka_prev = 0.0;
+    double vo_sum = 0.0, v_last = 0.0, dr_sum = 0.0, dr_last = 0.0;
+    const int half = Nt / 2;
+    const size_t fstride = (size_t)Nt * (size_t)Np;
+    double* sp = A.states + r;
+    const bool st_all = A.store_states != 0;
+    const bool st_xyt = st_all || A.keep_xyt;
+    // Simpson-rule terms
+    FrxSimpson S_acc, S_jerk, S_ori, S_len;
+    S_acc.part = S_acc.corr = S_jerk.part = S_jerk.corr = S_ori.part = S_ori.corr = S_len.part = S_len.corr = 0.0;
+    double a_prev = 0.0, thc_prev = 0.0;
+    const double alpha = (2 * dT * dT + 3 * dT * dT) / (6 * (dT + dT));
+    const double beta = (dT * dT + 3.0 * dT * dT) / (6 * dT);
+    const double eta = (1 * dT * dT * dT) / (6 * dT * (dT + dT));
+    const int nA = Nt, nbA = (nA & 1) ? nA : (nA - 1);            // integrands sampled at every step
+    const int nD = Nt - 1, nbD = (nD & 1) ? nD : (nD - 1);        // integrands built from np.diff
+
+    for (int i = 0; i < Nt; ++i) {
+        const double si = mt[M_S * TP + i], sdi = mt[M_SD * TP + i], sddi = mt[M_SDD * TP + i];
+        double di = 0, ddi = 0, dddi = 0;
+        if (i < traj_len) {
+            if (!low) {
+                double t = mt[M_T1 * TP + i], t2 = mt[M_T2 * TP + i], t3 = mt[M_T3 * TP + i], t4 = mt[M_T4 * TP + i],
+                       t5 = mt[M_T5 * TP + i];
+                di = poly_pos(Q, t, t2, t3, t4, t5);
+                ddi = poly_vel(Q, t, t2, t3, t4);
+                dddi = poly_acc(Q, t, t2, t3);
+            } else {
+                double q1 = si - s_first, q2 = q1 * q1, q3 = q2 * q1, q4 = q2 * q2, q5 = q4 * q1;
+                di = poly_pos(Q, q1, q2, q3, q4, q5);
+                ddi = poly_vel(Q, q1, q2, q3, q4);
+                dddi = poly_acc(Q, q1, q2, q3);
+            }
+        } else {
+            di = d_last;
+        }
+        double xi = 0.0, yi = 0.0, th_gl = 0.0, th_cl = 0.0, vi = 0.0, ai = 0.0, kappa = 0.0, kd = 0.0;
+        if (evaluate) {
+            double dp, dpp;
+            const bool mov = sdi > 0.001;
+            if (!low) {
+                dp = mov ? ddivf(ddi, sdi) : 0.;
+                double ddot = dddi - dp * sddi;
+                dpp = mov ? ddivf(ddot, sdi * sdi) : 0.;
+            } else {
+                dp = ddi; dpp = dddi;
+            }
+            const double interp = mt[M_INTERP * TP + i];
+            // :423-454 orientations; stand-still in high-velocity mode keeps the previous global orientation
+            const bool direct = mov || low;
+            if (direct) { th_cl = atan(dp); th_gl = th_cl + interp; }   // np.arctan2(dp, 1.0)
+            else { th_gl = th_prev; th_cl = th_gl - interp; }
+            // :457-478
+            const double k_r = mt[M_KR * TP + i], k_r_d = mt[M_KRD * TP + i];
+            double oneKrD = 1 - k_r * di;
+            // cos, tan and 1/cos of theta_cl.  On the direct branch theta_cl = atan(dp), so with w = 1 + dp^2:
+            // cos = 1/sqrt(w), 1/cos = sqrt(w), tan = dp hold algebraically (same <= 1-2 ulp error class as
+            // libm's cos/tan of the rounded angle); only the stand-still branch needs real trigonometry.
+            double cosT, tanT, secT;
+            if (direct) {
+                double w = 1.0 + dp * dp;
+                cosT = rsqrt(w);
+                secT = w * cosT;
+                tanT = dp;
+            } else {
+                double sT;
+                sincos(th_cl, &sT, &cosT);
+                secT = ddivg(1.0, cosT);
+                tanT = sT * secT;
+            }
+            double qc = oneKrD * secT;            // oneKrD / cos(theta_cl)
+            double cq = ddivg(1.0, qc);           // cos(theta_cl) / oneKrD
+            kappa = (dpp + (k_r * dp + k_r_d * di) * tanT) * cosT * (cq * cq) + cq * k_r;
+            vi = sdi * qc;
+            ai = sddi * qc + ((sdi * sdi) * secT) * (oneKrD * tanT * (kappa * qc - k_r) - (k_r_d * di + k_r * dp));
+            // :483-533 gates
+            uint32_t g = 0;
+            if (vi < -FRX_EPS) g |= 1u;
+            if (fabs(kappa) > A.kappa_max) g |= 2u;
+            double yaw_rate = (i > 0) ? ddivc(th_gl - th_prev, dT, A.inv_dt) : 0.;
+            double theta_dot_max = A.kappa_max * vi;
+            if (fabs(ddivc(rint(yaw_rate * 100000.0), 100000.0, 1e-5)) > theta_dot_max) g |= 4u;
+            double kappa_dot = (i > 0) ? ddivc(kappa - ka_prev, dT, A.inv_dt) : 0.;
+            if (fabs(kappa_dot) > 0.4) g |= 8u;
+            double a_hi = (vi > A.v_switch) ? ddivg(A.a_max * A.v_switch, vi) : A.a_max;
+            if (!(-A.a_max <= ai && ai <= a_hi)) g |= 16u;
+            if (brk) {
+                if (!gate_hit && g) { gate_or = g & (~g + 1u); gate_hit = true; }   // first violating step, its first gate only
+            } else {
+                gate_or |= g;
+            }
+            // :536-547 Cartesian position: zero from the first out-of-domain step on
+            if (i < first_none) {
+                xi = mt[M_PX * TP + i] - di * mt[M_SN * TP + i];
+                yi = mt[M_PY * TP + i] + di * mt[M_CS * TP + i];
+            }
+            kd = (i > 0) ? (kappa - ka_prev) : 0.0;   // np.append([0], np.diff(kappa_gl))
+            th_prev = th_gl;
+            ka_prev = kappa;
+        }
+        // running sums of the two default reductions (velocity_offset :120-130, distance_to_reference_path :154-169)
+        if (i >= half && i < Nt - 1) vo_sum += fabs(vi - A.v_des);
+        dr_sum += fabs(di);
+        if (i == Nt - 1) { v_last = vi; dr_last = di; }
+        if (XCOST) {
+            S_acc.add(i, nA, nbA, ai * ai, alpha, beta, eta);
+            S_len.add(i, nA, nbA, vi, alpha, beta, eta);
+            if (i > 0) {
+                double qa = ddivc(ai - a_prev, dT, A.inv_dt), qo = ddivc(th_cl - thc_prev, dT, A.inv_dt);
+                S_jerk.add(i - 1, nD, nbD, qa * qa, alpha, beta, eta);
+                S_ori.add(i - 1, nD, nbD, qo * qo, alpha, beta, eta);
+            }
+            a_prev = ai; thc_prev = th_cl;
+        }
+        // the 14 fields of this step: lanes = 32 consecutive candidates -> one coalesced 256-byte store each
+        double* p = sp + (size_t)i * (size_t)Np;
+        if (st_xyt) {           // x, y, theta are re-read by the obstacle pass: keep them in L2
+            __stcg(p, xi); __stcg(p + fstride, yi); __stcg(p + 2 * fstride, th_gl);
+        }
+        if (st_all) {
+            p += 3 * fstride;
+            __stcs(p, vi); p += fstride;
+            __stcs(p, ai); p += fstride;
+            __stcs(p, kappa); p += fstride;
+            __stcs(p, kd); p += fstride;
+            __stcs(p, si); p += fstride;
+            __stcs(p, di); p += fstride;
+            __stcs(p, th_cl); p += fstride;
+            __stcs(p, sdi); p += fstride;
+            __stcs(p, sddi); p += fstride;
+            __stcs(p, ddi); p += fstride;
+            __stcs(p, dddi);
+        }
+    }
+    if (evaluate) {
+        if (gate_or) {
+            feasible = false;
+            if (gate_or & 1u) reasons |= FRX_FLAG_REASON(4);
+            if (gate_or & 2u) reasons |= FRX_FLAG_REASON(5);
+            if (gate_or & 4u) reasons |= FRX_FLAG_REASON(6);
+            if (gate_or & 8u) reasons |= FRX_FLAG_REASON(7);
+            if (gate_or & 16u) reasons |= FRX_FLAG_REASON(8);
+        }
+        stored = feasible || draw;
+        in_list = stored;
+        if (stored && seen_none) { valid = false; reasons |= FRX_FLAG_REASON(9); }
+    }
+    const bool costed = draw ? in_list : (in_list && valid && feasible && stored);
+    const bool candidate = draw ? (in_list && feasible) : costed;
+
+    // ---------------- second pass over the steps, only for the lanes that need it: prediction cost
+    // (get_inv_mahalanobis_dist, collision_probability.py:264-299), distance_to_obstacles (:172-186) and the
+    // collision sweep (planner.py:329-378, collision_check.py:110-200); obstacle data is warp-uniform per step
+    double pred_sum = 0.0, d2o_sum = 0.0;
+    bool collide = false, boundary = false;
+    if (OBS || XCOST) {
+        const bool need_pred = OBS && costed && (cost_mask & (1u << FRX_COST_PREDICTION)) && A.O > 0;
+        const bool need_d2o = XCOST && costed && (cost_mask & (1u << FRX_COST_DISTANCE_TO_OBSTACLES)) && A.n_obs_pos > 0;
+        const bool need_col = OBS && candidate && A.check_collisions && (A.O > 0 || A.B > 0);
+        if (need_pred || need_d2o || need_col) {
+            const int OTP = A.Tp;       // step pitch of the obstacle table
+            double pbx = 0, pby = 0, pux = 0, puy = 0;   // ego box of the previous step
+            const double* q = sp;
+            for (int i = 0; i < Nt; ++i, q += Np) {
+                const double x = __ldcg(q), y = __ldcg(q + fstride);
+                if (need_pred && i >= 1) {
+                    for (int o = 0; o < A.O; ++o) {
+                        if (i >= __ldg(A.obs_len + o)) continue;
+                        const double* __restrict__ ob = A.obs + (size_t)o * (FRX_OBS_NARR * OTP) + (i - 1);
+                        double ex = x - __ldg(ob + OB_PX * OTP);
+                        double ey = y - __ldg(ob + OB_PY * OTP);
+                        double t0 = ex * __ldg(ob + OB_IV00 * OTP) + ey * __ldg(ob + OB_IV10 * OTP);
+                        double t1 = ex * __ldg(ob + OB_IV01 * OTP) + ey * __ldg(ob + OB_IV11 * OTP);
+                        double m = t0 * ex + t1 * ey;
+                        pred_sum += drcpg(m * m);
+                    }
+                }
+                if (need_d2o) {
+                    for (int o = 0; o < A.n_obs_pos; ++o) {
+                        double ex = x - __ldg(A.obs_pos + 2 * o), ey = y - __ldg(A.obs_pos + 2 * o + 1);
+                        double dist = sqrt(ex * ex + ey * ey);
+                        d2o_sum += ddivg(1.0, dist * dist);
+                    }
+                }
+                if (need_col) {
+                    double sn, cs;
+                    sincos(__ldcg(q + 2 * fstride), &sn, &cs);
+                    const double bx = x + A.wb_rear * cs, by = y + A.wb_rear * sn;     // state.py:30-39 rear axle -> centre
+                    if (i >= 1 && !(collide && (boundary || A.B == 0))) {
+                        const int k = i - 1;                                            // hull of boxes k, k + 1
+                        Hull e = obb_sum_hull(pbx, pby, pux, puy, bx, by, cs, sn, A.half_len, A.half_wid);
+                        const double er = sqrt(e.ha * e.ha + e.hb * e.hb) * (1.0 + 1e-9);
+                        if (k >= 1 && !collide) {
+                            for (int o = 0; o < A.O; ++o) {
+                                const int len = min(Nt, __ldg(A.obs_len + o));
+                                if (len <= 2 || k > len - 1) continue;
+                                const double* __restrict__ ob = A.obs + (size_t)o * (FRX_OBS_NARR * OTP) + (k - 1);
+                                double ocx = __ldg(ob + OB_HCX * OTP), ocy = __ldg(ob + OB_HCY * OTP);
+                                double rr = er + __ldg(ob + OB_HR * OTP);
+                                double ddx = ocx - e.cx, ddy = ocy - e.cy;
+                                if (ddx * ddx + ddy * ddy > rr * rr) continue;      // conservative broad phase
+                                if (obb_overlap(e, ocx, ocy, __ldg(ob + OB_HUX * OTP), __ldg(ob + OB_HUY * OTP),
+                                                __ldg(ob + OB_HHA * OTP), __ldg(ob + OB_HHB * OTP))) {
+                                    collide = true;
+                                    break;
+                                }
+                            }
+                        }
+                        if (!boundary) {
+                            for (int b = 0; b < A.B; ++b) {
+                                const double* __restrict__ sb = A.sobb + b * 8;
+                                double rr = er + __ldg(sb + 6);
+                                double ddx = __ldg(sb) - e.cx, ddy = __ldg(sb + 1) - e.cy;
+                                if (ddx * ddx + ddy * ddy > rr * rr) continue;
+                                if (obb_overlap(e, __ldg(sb), __ldg(sb + 1), __ldg(sb + 2), __ldg(sb + 3), __ldg(sb + 4), __ldg(sb + 5))) {
+                                    boundary = true;
+                                    break;
+                                }
+                            }
+                        }
+                    }
+                    pbx = bx; pby = by; pux = cs; puy = sn;
+                }
+            }
+        }
+    }
+
+    // ---------------- costs (cost_function.py:78-91, partial_cost_functions.py): weighted sum in name-sorted order
+    double total = 0.0;
+    double* cp = A.costs + (size_t)r * A.n_costs;
+    if (costed) {
+        for (int k = 0; k < A.n_costs; ++k) {
+            const int id = A.cost_ids[k];
+            double cv = 0.0;
+            switch (id) {
+                case FRX_COST_LATERAL_JERK: cv = sq_jerk_integral(Q, dT); break;
+                case FRX_COST_LONGITUDINAL_JERK: cv = H->jerk_lon; break;
+                case FRX_COST_VELOCITY_OFFSET: { double dv = v_last - A.v_des; cv = vo_sum + fabs(dv * dv); } break;   // :120-130
+                case FRX_COST_DISTANCE_TO_REFERENCE_PATH: cv = ddivc(dr_sum + fabs(dr_last) * 5, (double)Nt, A.inv_Nt); break;   // :154-169
+                case FRX_COST_PREDICTION: cv = pred_sum; break;
+                case FRX_COST_DISTANCE_TO_OBSTACLES: cv = d2o_sum; break;
+                case FRX_COST_ACCELERATION: cv = dT / 3.0 * S_acc.part + S_acc.corr; break;
+                case FRX_COST_JERK: cv = dT / 3.0 * S_jerk.part + S_jerk.corr; break;
+                case FRX_COST_ORIENTATION_OFFSET: cv = dT / 3.0 * S_ori.part + S_ori.corr; break;
+                case FRX_COST_PATH_LENGTH: cv = dT / 3.0 * S_len.part + S_len.corr; break;
+                default: break;
+            }
+            total += A.w[k] * cv;
+            cp[k] = cv;
+        }
+    } else {
+        for (int k = 0; k < A.n_costs; ++k) cp[k] = 0.0;
+    }
+
+    // ---------------- per-candidate scalars
+    uint32_t fl = reasons;
+    if (valid) fl |= FRX_FLAG_VALID;
+    if (feasible) fl |= FRX_FLAG_FEASIBLE;
+    if (stored) fl |= FRX_FLAG_STORED;
+    if (in_list) fl |= FRX_FLAG_IN_LIST;
+    if (costed) fl |= FRX_FLAG_COSTED;
+    if (candidate) fl |= FRX_FLAG_CANDIDATE;
+    if (collide) fl |= FRX_FLAG_COLLIDE;
+    if (boundary) fl |= FRX_FLAG_BOUNDARY;
+    A.total[r] = total;
+    A.flags[r] = fl;
+    A.traj_len[r] = traj_len;
+    // statistics (reactive_planner.py:229-235): one event bit per counter
+    unsigned ev = 0;
+    if (in_list) ev |= 1u << CNT_IN_LIST;
+    if (in_list && valid && feasible) ev |= 1u << CNT_FEASIBLE;
+    if (in_list && !(valid && feasible)) ev |= 1u << CNT_INFEASIBLE_IN_LIST;
+    if (candidate) ev |= 1u << CNT_CANDIDATES;
+    if (candidate && collide) ev |= 1u << CNT_COLLIDE;
+    if (candidate && boundary) ev |= 1u << CNT_BOUNDARY;
+    ev |= ((fl >> 2) & 0x3ffu) << CNT_REASON1;      // reason bits 1..10 -> slots CNT_REASON1..+9
+    out.ev = ev;
+    out.total = total;
+    out.winner_ok = candidate && !collide && !boundary;
+    return out;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// kernel body: prologue (TMA staging of the reference tables), tile loop, per-CTA / last-CTA arg-min
+// ------------------------------------------------------------------------------------------------------------
+template <bool OBS, bool XCOST>
+__device__ __forceinline__ void frx_tile_body(const FrxKernelArgs& A, const int cta_local, unsigned char* smem_raw) {
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const int Mpad = A.Mpad, TP = A.tpitch;
+    double* s_ref = reinterpret_cast<double*>(smem_raw);                    // [6][Mpad]
+    double* s_Ttab = s_ref + 6 * Mpad;                                       // [FRX_MAX_T_VALUES]
+    double* s_memo = s_Ttab + FRX_MAX_T_VALUES;                              // [WARPS][SLOTS][M_FIELDS][TP]
+    FrxMemoHdr* s_hdr = reinterpret_cast<FrxMemoHdr*>(s_memo + (size_t)FRX_WARPS_PER_CTA * FRX_MEMO_SLOTS * M_FIELDS * TP);
+    unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_hdr + FRX_WARPS_PER_CTA * FRX_MEMO_SLOTS);
+    FrxBest* s_best = reinterpret_cast<FrxBest*>(s_bar + 2);                 // [WARPS]
+
+    // ---- stage the reference tables with one TMA bulk copy (UBLKCP) guarded by an mbarrier
+    const uint32_t ref_bytes = (uint32_t)(6 * Mpad * sizeof(double));
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(s_bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(s_bar)), "r"(ref_bytes)
+                     : "memory");
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                smem_u32(s_ref)),
+            "l"(A.ref), "r"(ref_bytes), "r"(smem_u32(s_bar))
+            : "memory");
+    }
+    for (int k = threadIdx.x; k < FRX_MAX_T_VALUES; k += FRX_THREADS)
+        s_Ttab[k] = (k < A.nT) ? A.Ttab[k] : __longlong_as_double(0x7ff8000000000000LL);
+    if (lane < FRX_MEMO_SLOTS) s_hdr[wib * FRX_MEMO_SLOTS + lane].valid = 0;
+
+    unsigned cost_mask = 0;
+    for (int k = 0; k < A.n_costs; ++k) cost_mask |= 1u << A.cost_ids[k];
+    const long long N = A.N;
+    const long long n_tiles = (N + 31) >> 5;
+
+    // Work distribution: warps pull tiles of 32 consecutive rows from a global ticket counter; the ticket of the
+    // NEXT tile is requested one tile ahead so its latency is hidden.
+    unsigned long long next_tile = 0;
+    if (lane == 0) next_tile = atomicAdd(A.counters + CNT_WORK, 1ULL);
+
+    {   // wait for the bulk copy (phase 0)
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(done)
+                : "r"(smem_u32(s_bar))
+                : "memory");
+        }
+    }
+    __syncthreads();
+
+    double* memo = s_memo + (size_t)wib * FRX_MEMO_SLOTS * M_FIELDS * TP;
+    FrxMemoHdr* hdr = s_hdr + wib * FRX_MEMO_SLOTS;
+    double best_cost = __longlong_as_double(0x7ff0000000000000LL);  // +inf
+    long long best_idx = -1;
+    unsigned int my_cnt = 0;          // lane k counts event k (CNT_* enum), 32-bit is ample per warp
+    unsigned int t_missing = 0;
+
+    for (;;) {
+        const long long tile = (long long)__shfl_sync(FULL, next_tile, 0);
+        if (tile >= n_tiles) break;
+        if (lane == 0) next_tile = atomicAdd(A.counters + CNT_WORK, 1ULL);
+        const long long r = (tile << 5) + lane;
+        const bool in_range = r < N;
+        const long long rl = in_range ? r : (N - 1);
+        // ---------------- sampling row (sampling_matrix.py:85-121 column order)
+        double T, s0, ss0, sss0, ss1, d0, dd0, ddd0, d1, dd1, ddd1;
+        if (A.sampling != nullptr) {
+            const double* __restrict__ row = A.sampling + rl * 13;
+            T = __ldg(row + 1); s0 = __ldg(row + 2); ss0 = __ldg(row + 3); sss0 = __ldg(row + 4); ss1 = __ldg(row + 5);
+            d0 = __ldg(row + 7); dd0 = __ldg(row + 8); ddd0 = __ldg(row + 9); d1 = __ldg(row + 10); dd1 = __ldg(row + 11);
+            ddd1 = __ldg(row + 12);
+        } else {
+            const long long g = A.row_first + rl;
+            const long long per_t = (long long)A.g_nv * A.g_nd;
+            const int it = (int)(g / per_t);
+            const int rem = (int)(g - (long long)it * per_t);
+            const int iv = rem / A.g_nd, id = rem - iv * A.g_nd;
+            T = __ldg(A.g_t1 + it); ss1 = __ldg(A.g_v1 + iv); d1 = __ldg(A.g_d1 + id);
+            s0 = A.xcl[0]; ss0 = A.xcl[1]; sss0 = A.xcl[2]; d0 = A.xcl[3]; dd0 = A.xcl[4]; ddd0 = A.xcl[5];
+            dd1 = 0.0; ddd1 = 0.0;
+        }
+        // ---------------- passes of (at most) two memo keys each
+        unsigned todo = __ballot_sync(FULL, in_range);
+        while (todo) {
+            const int la = __ffs(todo) - 1;
+            const double aT = __shfl_sync(FULL, T, la), as0 = __shfl_sync(FULL, s0, la), ass0 = __shfl_sync(FULL, ss0, la),
+                         asss0 = __shfl_sync(FULL, sss0, la), ass1 = __shfl_sync(FULL, ss1, la);
+            const bool eqA = (T == aT) && (s0 == as0) && (ss0 == ass0) && (sss0 == asss0) && (ss1 == ass1);
+            const unsigned mA = (__ballot_sync(FULL, eqA) & todo) | (1u << la);
+            const unsigned rest = todo & ~mA;
+            unsigned mB = 0;
+            double bT = 0, bs0 = 0, bss0 = 0, bsss0 = 0, bss1 = 0;
+            if (rest) {
+                const int lb = __ffs(rest) - 1;
+                bT = __shfl_sync(FULL, T, lb); bs0 = __shfl_sync(FULL, s0, lb); bss0 = __shfl_sync(FULL, ss0, lb);
+                bsss0 = __shfl_sync(FULL, sss0, lb); bss1 = __shfl_sync(FULL, ss1, lb);
+                const bool eqB = (T == bT) && (s0 == bs0) && (ss0 == bss0) && (sss0 == bsss0) && (ss1 == bss1);
+                mB = (__ballot_sync(FULL, eqB) & rest) | (1u << lb);
+            }
+            // which slot holds which key (warp-uniform): reuse a slot filled for the same key by an earlier tile
+            int sa = -1, sb = -1;
+#pragma unroll
+            for (int s = 0; s < FRX_MEMO_SLOTS; ++s) {
+                const FrxMemoHdr& h = hdr[s];
+                if (h.valid) {
+                    if (h.key[0] == aT && h.key[1] == as0 && h.key[2] == ass0 && h.key[3] == asss0 && h.key[4] == ass1) sa = s;
+                    else if (mB && h.key[0] == bT && h.key[1] == bs0 && h.key[2] == bss0 && h.key[3] == bsss0 && h.key[4] == bss1) sb = s;
+                }
+            }
+            if (sa < 0) {
+                sa = (sb == 0) ? 1 : 0;
+                frx_memo_fill(A, s_ref, s_Ttab, memo + (size_t)sa * M_FIELDS * TP, hdr + sa, aT, as0, ass0, asss0, ass1);
+            }
+            if (mB && sb < 0) {
+                sb = 1 - sa;
+                frx_memo_fill(A, s_ref, s_Ttab, memo + (size_t)sb * M_FIELDS * TP, hdr + sb, bT, bs0, bss0, bsss0, bss1);
+            }
+            __syncwarp();
+            const unsigned pass = mA | mB;
+            FrxLaneOut o;
+            o.ev = 0; o.total = 0.0; o.winner_ok = false; o.t_missing = false;
+            if ((pass >> lane) & 1u) {
+                const int slot = ((mB >> lane) & 1u) ? sb : sa;
+                o = frx_candidate<OBS, XCOST>(A, cost_mask, r, T, d0, dd0, ddd0, d1, dd1, ddd1, memo + (size_t)slot * M_FIELDS * TP,
+                                              hdr + slot);
+            }
+            __syncwarp();
+            // the running arg-min (planner.py:384-392); rows of a lane only grow, so `<` keeps the lowest row
+            if (o.winner_ok && o.total < best_cost) { best_cost = o.total; best_idx = r; }
+            if (o.t_missing) t_missing++;
+            if (__any_sync(FULL, o.ev != 0)) {
+#pragma unroll
+                for (int e = 0; e < CNT_REASON1 + 10; ++e) {
+                    const unsigned m = __ballot_sync(FULL, (o.ev >> e) & 1u);
+                    if (lane == e) my_cnt += __popc(m);
+                }
+            }
+            todo &= ~pass;
+        }
+    }
+
+    // ---------------- per-warp, per-CTA reduction of (min cost, lowest row) and the counters
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const double oc = __shfl_xor_sync(FULL, best_cost, off);
+        const long long oi = __shfl_xor_sync(FULL, best_idx, off);
+        if (oi >= 0 && (best_idx < 0 || oc < best_cost || (oc == best_cost && oi < best_idx))) { best_cost = oc; best_idx = oi; }
+    }
+    t_missing = __reduce_add_sync(FULL, t_missing);
+    if (lane == 0) {
+        s_best[wib].cost = best_cost;
+        s_best[wib].idx = best_idx;
+        if (t_missing) atomicAdd(A.counters + CNT_T_NOT_FOUND, (unsigned long long)t_missing);
+    }
+    if (lane < CNT_REASON1 + 10 && my_cnt) atomicAdd(A.counters + lane, (unsigned long long)my_cnt);
+    __syncthreads();   // thread 0's fence below is cumulative over what the barrier made visible to it
+    __shared__ int s_is_last;
+    if (threadIdx.x == 0) {
+        FrxBest b = s_best[0];
+#pragma unroll
+        for (int w = 1; w < FRX_WARPS_PER_CTA; ++w) {
+            FrxBest o = s_best[w];
+            if (o.idx >= 0 && (b.idx < 0 || o.cost < b.cost || (o.cost == b.cost && o.idx < b.idx))) b = o;
+        }
+        A.blockbest[cta_local] = b;
+        __threadfence();
+        unsigned long long done = atomicAdd(A.counters + CNT_DONE, 1ULL);
+        s_is_last = (done == (unsigned long long)(A.n_cta - 1));
+    }
+    __syncthreads();
+    // ---------------- the last CTA of this plan reduces the per-CTA winners, publishes the result record to the
+    // mapped host struct (no memcpy node) and re-arms the counters for the next launch
+    if (s_is_last) {
+        __threadfence();
+        FrxBest b; b.cost = __longlong_as_double(0x7ff0000000000000LL); b.idx = -1;
+        for (int k = threadIdx.x; k < A.n_cta; k += FRX_THREADS) {
+            FrxBest o;
+            o.cost = __ldcg(&A.blockbest[k].cost);
+            o.idx = __ldcg(&A.blockbest[k].idx);
+            if (o.idx >= 0 && (b.idx < 0 || o.cost < b.cost || (o.cost == b.cost && o.idx < b.idx))) b = o;
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            FrxBest o;
+            o.cost = __shfl_xor_sync(FULL, b.cost, off);
+            o.idx = __shfl_xor_sync(FULL, b.idx, off);
+            if (o.idx >= 0 && (b.idx < 0 || o.cost < b.cost || (o.cost == b.cost && o.idx < b.idx))) b = o;
+        }
+        if (lane == 0) s_best[wib] = b;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            b = s_best[0];
+#pragma unroll
+            for (int w = 1; w < FRX_WARPS_PER_CTA; ++w) {
+                FrxBest o = s_best[w];
+                if (o.idx >= 0 && (b.idx < 0 || o.cost < b.cost || (o.cost == b.cost && o.idx < b.idx))) b = o;
+            }
+            if (b.idx >= 0) b.idx += A.row_base;   // the winner record carries the GLOBAL row index
+            *A.winner = b;
+            A.host_res->winner = b;
+        }
+        if (threadIdx.x < FRX_NUM_COUNTERS) {
+            unsigned long long v = atomicExch(A.counters + threadIdx.x, 0ULL);   // snapshot + reset in one step
+            A.host_res->counters[threadIdx.x] = v;
+        }
+        __threadfence_system();
+    }
+}
