@@ -26,6 +26,7 @@ void frx_launch_collision_counter(long long N, long long row_base, const double*
 void frx_launch_gather(const double* states, long long Np, int Nt, int Ntp, const long long* idx, long long first,
                        long long n_idx, uint32_t mask, double* out, cudaStream_t st);
 void frx_features(const FrxKernelArgs& a, bool* obs, bool* xcost);
+int frx_pick_seg(long long n_rows, int sm_count);
 
 void frx_launch_selftest_fdiv(long long n, const double* a, const double* b, double* q1, double* q2, cudaStream_t st);
 void frx_launch_selftest_divc(long long n, const double* a, double b, double* q1, double* q2, cudaStream_t st);
@@ -282,8 +283,8 @@ int frx_set_static_obbs(frx_ctx* ctx, int32_t B, const double* obb) {
 // ---- one plan = prepare (buffers + kernel arguments) -> launch -> finish (arg-min, read-back of the result)
 static int prepare_plan(frx_ctx* ctx, long long N, const double* d_sampling, bool grid_mode, int g_nv, int g_nd,
                         const double* d_t1, const double* d_v1, const double* d_d1, const double* xcl,
-                        long long row_first, long long row_base, int max_grid, cudaStream_t st, FrxKernelArgs* a_out,
-                        int* grid_out, int* nchunk_out) {
+                        long long row_first, long long row_base, int max_grid, int seg_hint, cudaStream_t st,
+                        FrxKernelArgs* a_out, int* grid_out, int* nchunk_out) {
     REQUIRE(ctx->have_params && ctx->have_ref && ctx->have_tables,
             "frx_plan: frx_set_params, frx_set_reference and frx_set_time_tables must be called first");
     const frx_params& p = ctx->prm;
@@ -310,7 +311,8 @@ static int prepare_plan(frx_ctx* ctx, long long N, const double* d_sampling, boo
         CK(cudaGetLastError());
         ctx->Tp = Tp;
     }
-    const long long n_tiles = (N + 31) / 32;       // one warp per tile of 32 rows
+    const int seg = (seg_hint > 0) ? seg_hint : frx_pick_seg(N, ctx->sm_count);
+    const long long n_tiles = (N + 32 / seg - 1) / (32 / seg);     // one warp per tile of 32 / seg rows
     long long want = (n_tiles + FRX_WARPS_PER_CTA - 1) / FRX_WARPS_PER_CTA;
     long long full = (max_grid > 0) ? max_grid : (long long)ctx->sm_count * ctx->occ_blocks;
     int grid = (int)(want < full ? want : full);
@@ -334,7 +336,7 @@ static int prepare_plan(frx_ctx* ctx, long long N, const double* d_sampling, boo
     if (xcl) for (int k = 0; k < 6; ++k) a.xcl[k] = xcl[k];
     a.row_first = row_first; a.row_base = row_base; a.N = N;
     a.states = ctx->states.p; a.costs = ctx->costs.p; a.total = ctx->total.p; a.flags = ctx->flags.p;
-    a.Np = Np; a.keep_xyt = (!p.store_states && need_xyt) ? 1 : 0;
+    a.seg = seg; a.Np = Np; a.keep_xyt = (!p.store_states && need_xyt) ? 1 : 0;
     a.traj_len = ctx->traj_len.p; a.blockbest = ctx->blockbest.p; a.counters = ctx->counters.p;
     a.winner = ctx->winner.p; a.host_res = ctx->d_res; a.n_cta = grid;
     if (ctx->counters_dirty) {
@@ -390,8 +392,8 @@ static int enqueue_plan(frx_ctx* ctx, long long N, const double* d_sampling, boo
     cudaStream_t st = ctx->stream;
     FrxKernelArgs a;
     int grid = 1, nchunk = 1;
-    int rc = prepare_plan(ctx, N, d_sampling, grid_mode, g_nv, g_nd, d_t1, d_v1, d_d1, xcl, row_first, row_base, 0, st, &a,
-                          &grid, &nchunk);
+    int rc = prepare_plan(ctx, N, d_sampling, grid_mode, g_nv, g_nd, d_t1, d_v1, d_d1, xcl, row_first, row_base, 0, 0, st,
+                          &a, &grid, &nchunk);
     if (rc != FRX_OK) return rc;
     ctx->counters_dirty = true;          // cleared again once the launch sequence has completed
     CK(cudaEventRecord(ctx->evk0, st));
@@ -506,13 +508,14 @@ int frx_plan_batched(int32_t n_agents, frx_ctx** ctxs, const int64_t* n_rows, co
         occ = b;
     }
     const long long budget = (long long)ctx->sm_count * occ;
+    const int batch_seg = frx_pick_seg(total_rows, ctx->sm_count);     // one kernel instance serves all agents
     for (int a = 0; a < n_agents; ++a) {
         frx_ctx* c = ctxs[a];
         long long share = (budget * n_rows[a] + total_rows - 1) / total_rows;
         if (share < 1) share = 1;
         int g = 1, nch = 1;
         int rc = prepare_plan(c, n_rows[a], c->sampling.p, false, 0, 0, nullptr, nullptr, nullptr, nullptr, 0, 0,
-                              (int)share, st, &args[a], &g, &nch);
+                              (int)share, batch_seg, st, &args[a], &g, &nch);
         if (rc != FRX_OK) { ctx->err = c->err; return rc; }
         if (nchunk0 < 0) nchunk0 = nch;
         REQUIRE(nch == nchunk0, "frx_plan_batched: all agents must share the planning horizon (samples per candidate)");

@@ -88,6 +88,7 @@ struct FrxKernelArgs {
     // ---- outputs
     double* states;         // [14][Nt][Np]: field, step, candidate (candidate fastest, Np = N rounded up to 32)
     long long Np;
+    int seg;                // lanes per candidate (1, 2 or 4): which kernel instance runs, tile = 32 / seg rows
     int keep_xyt;           // store_states == 0 but the obstacle pass needs the x, y, theta planes
     double* costs;          // [N][n_costs]
     double* total;          // [N]

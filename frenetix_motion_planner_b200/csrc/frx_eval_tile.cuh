@@ -1,6 +1,13 @@
 // frx_eval_tile.cuh -- the eval kernel body: ONE THREAD PER CANDIDATE TRAJECTORY, one warp per tile of 32
 // consecutive sampling rows (included by frx_kernels.cu, which provides the arithmetic helpers).
 //
+//   * SEG lanes per candidate (SEG = 1, 2 or 4, picked from the row count): a warp works on a tile of C = 32 / SEG
+//     consecutive rows, lane = (segment, candidate), each lane walks its own contiguous segment of the time steps.
+//     With few rows (50,000 rows are only 1,563 warps of 32) the extra warps are what hides the fp64 dependency
+//     chains; with many rows SEG = 1 does the least redundant work.  Segment boundaries: the yaw-rate / curvature-
+//     rate gates and kappa diff of a segment's first step need the previous step, which another lane computes --
+//     they are evaluated after the loop from shuffled values; the stand-still heading carry is resolved in the
+//     prologue from the memo (which steps are stand-still depends on s(t) only);
 //   * lane = candidate: the polynomial coefficient solve, the per-candidate bookkeeping and the cost assembly are
 //     per-thread scalar code (useful work in all 32 lanes), the time-step loop runs sequentially in each thread --
 //     time-coupled quantities (yaw rate, curvature rate, stand-still heading carry) are plain registers, no
@@ -182,11 +189,16 @@ struct FrxLaneOut {
     bool t_missing;
 };
 
-template <bool OBS, bool XCOST>
-__device__ __forceinline__ FrxLaneOut frx_candidate(const FrxKernelArgs& A, const unsigned cost_mask, const long long r,
-                                                    const double T, const double d0, const double dd0, const double ddd0,
-                                                    const double d1, const double dd1, const double ddd1,
+// `pass` = the lanes executing this call together (all SEG lanes of a candidate are among them): the mask of every
+// shuffle below, which all of them reach -- there is no early return.
+template <int SEG, bool OBS, bool XCOST>
+__device__ __forceinline__ FrxLaneOut frx_candidate(const FrxKernelArgs& A, const unsigned cost_mask, const unsigned pass,
+                                                    const long long r, const double T, const double d0, const double dd0,
+                                                    const double ddd0, const double d1, const double dd1, const double ddd1,
                                                     const double* __restrict__ mt, const FrxMemoHdr* __restrict__ H) {
+    constexpr int C = 32 / SEG;                 // candidates per tile
+    const int lane = threadIdx.x & 31;
+    const int cand = lane & (C - 1), seg = lane / C;
     FrxLaneOut out;
     out.ev = 0; out.total = 0.0; out.winner_ok = false; out.t_missing = false;
     const int Nt = A.Nt, TP = A.tpitch;
@@ -195,11 +207,11 @@ __device__ __forceinline__ FrxLaneOut frx_candidate(const FrxKernelArgs& A, cons
     const bool low = A.low != 0, draw = A.draw != 0, debug = A.debug != 0;
     const bool brk = !draw && !debug;
     const int hbits = H->bits;
-    if (hbits & 4) {
-        A.flags[r] = 0u; A.total[r] = 0.0; A.traj_len[r] = 0;
-        out.t_missing = true;
-        return out;
-    }
+    const bool dead = (hbits & 4) != 0;         // duration missing from the time tables: reported, row marked dead
+    // this lane's segment of the time steps
+    const int seglen = (Nt + SEG - 1) / SEG;
+    const int i0 = seg * seglen;
+    const int i1 = dead ? i0 : ((i0 + seglen < Nt) ? (i0 + seglen) : Nt);
     const int traj_len = H->traj_len;
     const int il = traj_len - 1;
     const bool any_neg = (hbits & 1) != 0, any_acc = (hbits & 2) != 0;
@@ -220,7 +232,7 @@ __device__ __forceinline__ FrxLaneOut frx_candidate(const FrxKernelArgs& A, cons
         Q.c5 = ddivf((6 * b0 - (3 * b1) * tau) + (0.5 * b2) * u2, u5);
     }
     double d_last = 0.0;
-    if (traj_len < Nt) {
+    if (traj_len < Nt && !dead) {
         if (!low) {
             d_last = poly_pos(Q, mt[M_T1 * TP + il], mt[M_T2 * TP + il], mt[M_T3 * TP + il], mt[M_T4 * TP + il], mt[M_T5 * TP + il]);
         } else {
@@ -242,7 +254,7 @@ __device__ __forceinline__ FrxLaneOut frx_candidate(const FrxKernelArgs& A, cons
         if (any_acc) { feasible = false; reasons |= FRX_FLAG_REASON(1); stored = false; }
         else if (any_neg) { feasible = false; reasons |= FRX_FLAG_REASON(2); stored = false; }
     }
-    const bool evaluate = in_list && stored;    // reaches the per-step loop of :389
+    const bool evaluate = in_list && stored && !dead;    // reaches the per-step loop of :389
 
     // ---------------- the time-step loop: lateral samples (:325-346), back-projection + gates (:389-533), x/y
     //                  (:536-547), running cost sums, 14 coalesced stores per step
@@ -252,6 +264,21 @@ __device__ __forceinline__ FrxLaneOut frx_candidate(const FrxKernelArgs& A, cons
     const bool seen_none = evaluate && (first_none < Nt);
     double th_prev = A.x0_orientation;   // theta_gl[i-1]
     double ka_prev = 0.0;
+    // first step of a later segment: gates that need step i0 - 1 are completed after the loop
+    uint32_t g_first = 0;
+    double th_first = 0.0, ka_first = 0.0, vi_first = 0.0, a_first = 0.0, thc_first = 0.0;
+    if (SEG > 1 && seg > 0 && evaluate && !low && i0 < i1 && !(mt[M_SD * TP + i0] > 0.001)) {
+        // the segment starts in stand-still: theta_gl of the last moving step before it (:423-454), or x_0's
+        for (int j = i0 - 1; j >= 0; --j) {
+            const double sdj = mt[M_SD * TP + j];
+            if (sdj > 0.001) {
+                double ddj = 0.0;
+                if (j < traj_len) ddj = poly_vel(Q, mt[M_T1 * TP + j], mt[M_T2 * TP + j], mt[M_T3 * TP + j], mt[M_T4 * TP + j]);
+                th_prev = atan(ddivf(ddj, sdj)) + mt[M_INTERP * TP + j];
+                break;
+            }
+        }
+    }
     double vo_sum = 0.0, v_last = 0.0, dr_sum = 0.0, dr_last = 0.0;
     const int half = Nt / 2;
     const size_t fstride = (size_t)Nt * (size_t)Np;
@@ -268,7 +295,7 @@ __device__ __forceinline__ FrxLaneOut frx_candidate(const FrxKernelArgs& A, cons
     const int nA = Nt, nbA = (nA & 1) ? nA : (nA - 1);            // integrands sampled at every step
     const int nD = Nt - 1, nbD = (nD & 1) ? nD : (nD - 1);        // integrands built from np.diff
 
-    for (int i = 0; i < Nt; ++i) {
+    for (int i = i0; i < i1; ++i) {
         const double si = mt[M_S * TP + i], sdi = mt[M_SD * TP + i], sddi = mt[M_SDD * TP + i];
         double di = 0, ddi = 0, dddi = 0;
         if (i < traj_len) {
@@ -330,14 +357,18 @@ __device__ __forceinline__ FrxLaneOut frx_candidate(const FrxKernelArgs& A, cons
             uint32_t g = 0;
             if (vi < -FRX_EPS) g |= 1u;
             if (fabs(kappa) > A.kappa_max) g |= 2u;
-            double yaw_rate = (i > 0) ? ddivc(th_gl - th_prev, dT, A.inv_dt) : 0.;
+            const bool deferred = (SEG > 1) && (i == i0) && (seg > 0);
+            const bool has_prev = (i > 0) && !deferred;
+            double yaw_rate = has_prev ? ddivc(th_gl - th_prev, dT, A.inv_dt) : 0.;
             double theta_dot_max = A.kappa_max * vi;
             if (fabs(ddivc(rint(yaw_rate * 100000.0), 100000.0, 1e-5)) > theta_dot_max) g |= 4u;
-            double kappa_dot = (i > 0) ? ddivc(kappa - ka_prev, dT, A.inv_dt) : 0.;
+            double kappa_dot = has_prev ? ddivc(kappa - ka_prev, dT, A.inv_dt) : 0.;
             if (fabs(kappa_dot) > 0.4) g |= 8u;
             double a_hi = (vi > A.v_switch) ? ddivg(A.a_max * A.v_switch, vi) : A.a_max;
             if (!(-A.a_max <= ai && ai <= a_hi)) g |= 16u;
-            if (brk) {
+            if (deferred) {
+                g_first = g; th_first = th_gl; ka_first = kappa; vi_first = vi; a_first = ai; thc_first = th_cl;
+            } else if (brk) {
                 if (!gate_hit && g) { gate_or = g & (~g + 1u); gate_hit = true; }   // first violating step, its first gate only
             } else {
                 gate_or |= g;
@@ -347,7 +378,7 @@ __device__ __forceinline__ FrxLaneOut frx_candidate(const FrxKernelArgs& A, cons
                 xi = mt[M_PX * TP + i] - di * mt[M_SN * TP + i];
                 yi = mt[M_PY * TP + i] + di * mt[M_CS * TP + i];
             }
-            kd = (i > 0) ? (kappa - ka_prev) : 0.0;   // np.append([0], np.diff(kappa_gl))
+            kd = has_prev ? (kappa - ka_prev) : 0.0;   // np.append([0], np.diff(kappa_gl))
             th_prev = th_gl;
             ka_prev = kappa;
         }
@@ -358,7 +389,7 @@ __device__ __forceinline__ FrxLaneOut frx_candidate(const FrxKernelArgs& A, cons
         if (XCOST) {
             S_acc.add(i, nA, nbA, ai * ai, alpha, beta, eta);
             S_len.add(i, nA, nbA, vi, alpha, beta, eta);
-            if (i > 0) {
+            if (i > i0 || (i > 0 && seg == 0)) {
                 double qa = ddivc(ai - a_prev, dT, A.inv_dt), qo = ddivc(th_cl - thc_prev, dT, A.inv_dt);
                 S_jerk.add(i - 1, nD, nbD, qa * qa, alpha, beta, eta);
                 S_ori.add(i - 1, nD, nbD, qo * qo, alpha, beta, eta);
@@ -385,6 +416,51 @@ __device__ __forceinline__ FrxLaneOut frx_candidate(const FrxKernelArgs& A, cons
             __stcs(p, dddi);
         }
     }
+    if (SEG > 1) {
+        // ---- segment boundaries: the previous segment's last step completes this segment's first one
+        const double th_in = __shfl_up_sync(pass, th_prev, C), ka_in = __shfl_up_sync(pass, ka_prev, C);
+        if (seg > 0 && evaluate && i0 < i1) {
+            double yaw_rate = ddivc(th_first - th_in, dT, A.inv_dt);
+            if (fabs(ddivc(rint(yaw_rate * 100000.0), 100000.0, 1e-5)) > A.kappa_max * vi_first) g_first |= 4u;
+            double kappa_dot = ddivc(ka_first - ka_in, dT, A.inv_dt);
+            if (fabs(kappa_dot) > 0.4) g_first |= 8u;
+            if (st_all) __stcs(sp + (size_t)FRX_F_KAPPA_DOT * fstride + (size_t)i0 * (size_t)Np, ka_first - ka_in);
+        }
+        if (XCOST) {
+            const double a_in = __shfl_up_sync(pass, a_prev, C), thc_in = __shfl_up_sync(pass, thc_prev, C);
+            if (seg > 0 && i0 < i1) {
+                // !evaluate lanes carry zeros here like in the loop
+                double qa = ddivc((evaluate ? a_first : 0.0) - a_in, dT, A.inv_dt);
+                double qo = ddivc((evaluate ? thc_first : 0.0) - thc_in, dT, A.inv_dt);
+                S_jerk.add(i0 - 1, nD, nbD, qa * qa, alpha, beta, eta);
+                S_ori.add(i0 - 1, nD, nbD, qo * qo, alpha, beta, eta);
+            }
+        }
+        // ---- this segment's verdict, then the candidate's: first violating step wins (brk) / union of all gates
+        uint32_t loc = brk ? (g_first ? (g_first & (~g_first + 1u)) : gate_or) : (g_first | gate_or);
+        uint32_t all = 0;
+#pragma unroll
+        for (int sgm = 0; sgm < SEG; ++sgm) {
+            const uint32_t v = __shfl_sync(pass, loc, cand + sgm * C);
+            if (brk) { if (!all) all = v; } else all |= v;
+        }
+        gate_or = all;
+        // ---- running sums
+#pragma unroll
+        for (int off = C; off < 32; off <<= 1) {
+            vo_sum += __shfl_xor_sync(pass, vo_sum, off);
+            dr_sum += __shfl_xor_sync(pass, dr_sum, off);
+            if (XCOST) {
+                S_acc.part += __shfl_xor_sync(pass, S_acc.part, off); S_acc.corr += __shfl_xor_sync(pass, S_acc.corr, off);
+                S_jerk.part += __shfl_xor_sync(pass, S_jerk.part, off); S_jerk.corr += __shfl_xor_sync(pass, S_jerk.corr, off);
+                S_ori.part += __shfl_xor_sync(pass, S_ori.part, off); S_ori.corr += __shfl_xor_sync(pass, S_ori.corr, off);
+                S_len.part += __shfl_xor_sync(pass, S_len.part, off); S_len.corr += __shfl_xor_sync(pass, S_len.corr, off);
+            }
+        }
+        const int owner = cand + ((Nt - 1) / seglen) * C;     // the lane whose segment holds the last step
+        v_last = __shfl_sync(pass, v_last, owner);
+        dr_last = __shfl_sync(pass, dr_last, owner);
+    }
     if (evaluate) {
         if (gate_or) {
             feasible = false;
@@ -406,6 +482,7 @@ __device__ __forceinline__ FrxLaneOut frx_candidate(const FrxKernelArgs& A, cons
     // collision sweep (planner.py:329-378, collision_check.py:110-200); obstacle data is warp-uniform per step
     double pred_sum = 0.0, d2o_sum = 0.0;
     bool collide = false, boundary = false;
+    if (SEG > 1 && (OBS || XCOST)) __syncwarp(pass);     // the x, y, theta planes of the other segments are visible now
     if (OBS || XCOST) {
         const bool need_pred = OBS && costed && (cost_mask & (1u << FRX_COST_PREDICTION)) && A.O > 0;
         const bool need_d2o = XCOST && costed && (cost_mask & (1u << FRX_COST_DISTANCE_TO_OBSTACLES)) && A.n_obs_pos > 0;
@@ -413,8 +490,14 @@ __device__ __forceinline__ FrxLaneOut frx_candidate(const FrxKernelArgs& A, cons
         if (need_pred || need_d2o || need_col) {
             const int OTP = A.Tp;       // step pitch of the obstacle table
             double pbx = 0, pby = 0, pux = 0, puy = 0;   // ego box of the previous step
-            const double* q = sp;
-            for (int i = 0; i < Nt; ++i, q += Np) {
+            if (SEG > 1 && need_col && i0 >= 1 && i0 < i1) {      // ... which another lane wrote for a later segment
+                const double* qp = sp + (size_t)(i0 - 1) * (size_t)Np;
+                double sn, cs;
+                sincos(__ldcg(qp + 2 * fstride), &sn, &cs);
+                pbx = __ldcg(qp) + A.wb_rear * cs; pby = __ldcg(qp + fstride) + A.wb_rear * sn; pux = cs; puy = sn;
+            }
+            const double* q = sp + (size_t)i0 * (size_t)Np;
+            for (int i = i0; i < i1; ++i, q += Np) {
                 const double x = __ldcg(q), y = __ldcg(q + fstride);
                 if (need_pred && i >= 1) {
                     for (int o = 0; o < A.O; ++o) {
@@ -478,6 +561,27 @@ __device__ __forceinline__ FrxLaneOut frx_candidate(const FrxKernelArgs& A, cons
         }
     }
 
+    if (SEG > 1 && (OBS || XCOST)) {
+#pragma unroll
+        for (int off = C; off < 32; off <<= 1) {
+            if (OBS) pred_sum += __shfl_xor_sync(pass, pred_sum, off);
+            if (XCOST) d2o_sum += __shfl_xor_sync(pass, d2o_sum, off);
+        }
+        if (OBS) {
+            unsigned cm2 = __ballot_sync(pass, collide), bm2 = __ballot_sync(pass, boundary);
+            unsigned mine = 0;
+#pragma unroll
+            for (int sgm = 0; sgm < SEG; ++sgm) mine |= 1u << (cand + sgm * C);
+            collide = (cm2 & mine) != 0;
+            boundary = (bm2 & mine) != 0;
+        }
+    }
+    if (dead) {
+        if (seg == 0) { A.flags[r] = 0u; A.total[r] = 0.0; A.traj_len[r] = 0; out.t_missing = true; }
+        return out;
+    }
+    if (SEG > 1 && seg != 0) return out;     // one lane per candidate writes the scalars and reports
+
     // ---------------- costs (cost_function.py:78-91, partial_cost_functions.py): weighted sum in name-sorted order
     double total = 0.0;
     double* cp = A.costs + (size_t)r * A.n_costs;
@@ -536,7 +640,7 @@ __device__ __forceinline__ FrxLaneOut frx_candidate(const FrxKernelArgs& A, cons
 // ------------------------------------------------------------------------------------------------------------
 // kernel body: prologue (TMA staging of the reference tables), tile loop, per-CTA / last-CTA arg-min
 // ------------------------------------------------------------------------------------------------------------
-template <bool OBS, bool XCOST>
+template <int SEG, bool OBS, bool XCOST>
 __device__ __forceinline__ void frx_tile_body(const FrxKernelArgs& A, const int cta_local, unsigned char* smem_raw) {
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
@@ -571,9 +675,10 @@ __device__ __forceinline__ void frx_tile_body(const FrxKernelArgs& A, const int 
     unsigned cost_mask = 0;
     for (int k = 0; k < A.n_costs; ++k) cost_mask |= 1u << A.cost_ids[k];
     const long long N = A.N;
-    const long long n_tiles = (N + 31) >> 5;
+    constexpr int C = 32 / SEG;
+    const long long n_tiles = (N + C - 1) / C;
 
-    // Work distribution: warps pull tiles of 32 consecutive rows from a global ticket counter; the ticket of the
+    // Work distribution: warps pull tiles of C consecutive rows from a global ticket counter; the ticket of the
     // NEXT tile is requested one tile ahead so its latency is hidden.
     unsigned long long next_tile = 0;
     if (lane == 0) next_tile = atomicAdd(A.counters + CNT_WORK, 1ULL);
@@ -601,7 +706,7 @@ __device__ __forceinline__ void frx_tile_body(const FrxKernelArgs& A, const int 
         const long long tile = (long long)__shfl_sync(FULL, next_tile, 0);
         if (tile >= n_tiles) break;
         if (lane == 0) next_tile = atomicAdd(A.counters + CNT_WORK, 1ULL);
-        const long long r = (tile << 5) + lane;
+        const long long r = tile * C + (lane & (C - 1));
         const bool in_range = r < N;
         const long long rl = in_range ? r : (N - 1);
         // ---------------- sampling row (sampling_matrix.py:85-121 column order)
@@ -663,7 +768,7 @@ __device__ __forceinline__ void frx_tile_body(const FrxKernelArgs& A, const int 
             o.ev = 0; o.total = 0.0; o.winner_ok = false; o.t_missing = false;
             if ((pass >> lane) & 1u) {
                 const int slot = ((mB >> lane) & 1u) ? sb : sa;
-                o = frx_candidate<OBS, XCOST>(A, cost_mask, r, T, d0, dd0, ddd0, d1, dd1, ddd1, memo + (size_t)slot * M_FIELDS * TP,
+                o = frx_candidate<SEG, OBS, XCOST>(A, cost_mask, pass, r, T, d0, dd0, ddd0, d1, dd1, ddd1, memo + (size_t)slot * M_FIELDS * TP,
                                               hdr + slot);
             }
             __syncwarp();

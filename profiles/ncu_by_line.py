@@ -16,7 +16,7 @@ src_csv, dis, sym = sys.argv[1:4]
 top_n = int(sys.argv[4]) if len(sys.argv) > 4 else 40
 body_lo = int(sys.argv[5]) if len(sys.argv) > 5 else 0
 body_hi = int(sys.argv[6]) if len(sys.argv) > 6 else 10 ** 9
-KERNEL_FILE = "frx_kernels.cu"
+KERNEL_FILES = ("frx_eval_tile.cuh", "frx_kernels.cu")   # attribution preference: body first, helpers second
 
 off2 = {}
 chain = []
@@ -41,13 +41,15 @@ for l in open(dis):
     if m:
         fresh = True
         body = None
-        for f, ln in chain:
-            if f == KERNEL_FILE and body_lo <= ln <= body_hi:
-                body = ln
+        for kf in KERNEL_FILES:
+            for f, ln in chain:
+                if f == kf and (kf != KERNEL_FILES[0] or body_lo <= ln <= body_hi):
+                    body = (kf, ln)
+                    break
+            if body is not None:
                 break
         leaf = chain[0] if chain else (None, None)
-        off2[int(m.group(1), 16)] = (body if body is not None else (leaf[1] if leaf[0] == KERNEL_FILE else None),
-                                     leaf, m.group(2).strip())
+        off2[int(m.group(1), 16)] = (body, leaf, m.group(2).strip())
 
 rows = list(csv.reader(open(src_csv)))
 hdr = rows[1]
@@ -84,9 +86,10 @@ for r in rows[2:]:
 print("total warp instructions", tot, " samples", tot_s)
 print("stalls:", ", ".join(f"{h[6:]}={100*v/max(tot_s,1):.1f}%" for h, v in stall_tot.most_common(9)))
 print("opcodes (dynamic):", ", ".join(f"{o}={100*n/tot:.1f}%/{100*ops_s[o]/max(tot_s,1):.1f}%s" for o, n in ops.most_common(24)))
-srcl = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'frenetix_motion_planner_b200', 'csrc',
-                         KERNEL_FILE)).read().split('\n')
+srcl = {kf: open(os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'frenetix_motion_planner_b200', 'csrc',
+                             kf)).read().split('\n') for kf in KERNEL_FILES}
 for line, (n, s, t) in sorted(by.items(), key=lambda kv: -kv[1][1])[:top_n]:
-    txt = srcl[line - 1].strip()[:90] if line else '?'
     top = ",".join(f"{h[6:]}:{v}" for h, v in stall_by_line[line].most_common(3))
+    txt = srcl[line[0]][line[1] - 1].strip()[:90] if line else '?'
+    line = f"{line[0][4:8]}:{line[1]}" if line else None
     print(f"{n:>9} {100*n/tot:5.1f}%i {100*s/max(tot_s,1):5.1f}%s thr={t/max(n,1):4.1f} [{top}] L{line}: {txt}")
