@@ -422,7 +422,8 @@ def main():
         cost, row, owner = (r.min_cost, r.argmin, 0) if ex is None else ex.exchange(r.min_cost, r.argmin, handler=h)
         win = None
         if row >= 0 and owner == rank:
-            win = h.get_states(np.array([row - first], dtype=np.int64))     # D2H of the selected trajectory
+            # the selected trajectory: published by the eval kernel with the arg-min (mapped result record)
+            win = h.winner_states() if row == r.argmin else h.get_states(np.array([row - first], dtype=np.int64))
         return r, row, win
 
     with torch.cuda.stream(stream):
@@ -469,8 +470,10 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
+        e2e_kern_ms, e2e_dev_ms = [], []
         for i in range(args.steps):
             r_e2e, row_e2e, win = step_e2e()
+            e2e_kern_ms.append(r_e2e.eval_kernel_ms); e2e_dev_ms.append(r_e2e.total_device_ms)
         stream.synchronize()
         torch.cuda.synchronize()
         e2e_s = time.perf_counter() - t0
@@ -522,7 +525,12 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT,
                     "h2d_bytes_per_step": int(0 if grid_mode else count * 13 * 8),
                     "d2h_bytes_per_step": int(16 + 8 * 17 + 14 * 32 * 8),
-                    "note": "frx_plan on pinned host rows (H2D inside) + result record + selected trajectory D2H, wall clock"},
+                    "ms_per_step": 1e3 * e2e_s / args.steps, "eval_kernel_ms": float(np.mean(e2e_kern_ms)),
+                    "device_ms": float(np.mean(e2e_dev_ms)),
+                    "note": "frx_plan on a PINNED HOST sampling matrix: the eval kernel reads the rows in place over PCIe "
+                            "(cp.async prefetch one tile ahead, no staging copy; FRX_ZEROCOPY=0 restores cudaMemcpyAsync), "
+                            "the result record and the selected trajectory's 14 state rows come back through mapped host "
+                            "memory written by the kernel's last CTA; wall clock around the C-ABI call"},
             "gpu_launches": gpu_launches, "clocks": clocks,
             "selected": {"row": int(row_e2e), "n_feasible": int(r_e2e.n_feasible), "n_collide": int(r_e2e.n_collide)},
         }

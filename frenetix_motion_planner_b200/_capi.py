@@ -65,7 +65,7 @@ class FrxResult(C.Structure):
 EXPORTS = ("frx_abi_version", "frx_create", "frx_destroy", "frx_last_error", "frx_set_reference", "frx_set_params",
            "frx_set_time_tables", "frx_set_predictions", "frx_set_obstacle_positions", "frx_set_static_obbs",
            "frx_plan", "frx_plan_device", "frx_plan_device_async", "frx_plan_wait", "frx_plan_grid", "frx_plan_batched", "frx_state_pitch", "frx_get_states",
-           "frx_get_states_range", "frx_get_costs", "frx_get_flags", "frx_device_pointers", "frx_winner_device_pointer",
+           "frx_get_states_range", "frx_winner_states", "frx_get_costs", "frx_get_flags", "frx_device_pointers", "frx_winner_device_pointer",
            "frx_selftest_fdiv", "frx_selftest_divc", "frx_set_stream",
            "frx_synchronize")
 
@@ -108,6 +108,7 @@ def load_library(path: Optional[str] = None):
     lib.frx_state_pitch.argtypes = [vp]; lib.frx_state_pitch.restype = C.c_int32
     lib.frx_get_states.argtypes = [vp, C.c_int64, C.POINTER(C.c_int64), C.c_uint32, dp]
     lib.frx_get_states_range.argtypes = [vp, C.c_int64, C.c_int64, C.c_uint32, dp]
+    lib.frx_winner_states.argtypes = [vp, C.c_uint32, dp]
     lib.frx_get_costs.argtypes = [vp, C.c_int64, C.c_int64, dp, dp]
     lib.frx_get_flags.argtypes = [vp, C.c_int64, C.c_int64, C.POINTER(C.c_uint32), ip]
     lib.frx_device_pointers.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
@@ -297,6 +298,16 @@ class Handler:
         out = np.empty((nf, idx.size, pitch), dtype=np.float64)
         self._check(self._lib.frx_get_states(self._ctx, idx.size, idx.ctypes.data_as(C.POINTER(C.c_int64)), mask, _dptr(out)))
         return out[:, :, :self.Nt]
+
+    def winner_states(self, fields=None) -> np.ndarray:
+        """State rows of the selected candidate of the last plan -> array [n_fields, Nt]; host-side copy out of the
+        mapped result record (no device round trip)."""
+        mask = self._mask(fields)
+        nf = bin(mask).count("1")
+        pitch = self.state_pitch()
+        out = np.empty((nf, pitch), dtype=np.float64)
+        self._check(self._lib.frx_winner_states(self._ctx, mask, _dptr(out)))
+        return out[:, :self.Nt]
 
     def get_states_range(self, first=0, count=None, fields=None) -> np.ndarray:
         count = self.n_rows - first if count is None else count

@@ -1,5 +1,6 @@
 // frx_capi.cu -- the C ABI (include/frx.h) over the sm_100a kernels.  Host C++ only; no torch types.
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include <math.h>
 #include <stdint.h>
 #include <string.h>
@@ -20,6 +21,8 @@ cudaError_t frx_launch_eval_batched(const FrxKernelArgs* h_agents, const FrxKern
 void frx_launch_obstacle_prep(int O, int T, int Tp, const double* pos, const double* cov, const double* theta,
                               const double* hl, const double* hw, double* obs, cudaStream_t st);
 void frx_launch_static_prep(int B, const double* obb, double* out, cudaStream_t st);
+void frx_launch_obstacle_compact(int O, int Tp, int Nt, const double* obs, const int* obs_len, double* pred, double* hull,
+                                 int* n_pred, int* n_hull, cudaStream_t st);
 void frx_launch_argmin(const FrxBest* bb, int nblocks, long long row_base, FrxBest* out, cudaStream_t st);
 void frx_launch_collision_counter(long long N, long long row_base, const double* total, const uint32_t* flags,
                                   const FrxBest* winner, unsigned long long* counters, int grid, cudaStream_t st);
@@ -66,6 +69,7 @@ struct frx_ctx {
 
     DevBuf<double> ref; int M = 0, Mpad = 0;
     DevBuf<double> Ttab; DevBuf<int> Tlen; DevBuf<double> tpow; int nT = 0, tpitch = 0;
+    DevBuf<double> opred, ohull; DevBuf<int> on_pred, on_hull; int compact_Nt = 0;
     DevBuf<double> obs, raw_pos, raw_cov, raw_theta, raw_hl, raw_hw; DevBuf<int> obs_len; int O = 0, T = 0, Tp = 0;
     DevBuf<double> obs_pos; int n_obs_pos = 0;
     DevBuf<double> sobb, raw_sobb; int B = 0;
@@ -144,6 +148,7 @@ int frx_destroy(frx_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
     ctx->ref.release(); ctx->Ttab.release(); ctx->Tlen.release(); ctx->tpow.release();
+    ctx->opred.release(); ctx->ohull.release(); ctx->on_pred.release(); ctx->on_hull.release();
     ctx->obs.release(); ctx->raw_pos.release(); ctx->raw_cov.release(); ctx->raw_theta.release();
     ctx->raw_hl.release(); ctx->raw_hw.release(); ctx->obs_len.release(); ctx->obs_pos.release();
     ctx->sobb.release(); ctx->raw_sobb.release(); ctx->sampling.release(); ctx->grid.release();
@@ -310,6 +315,16 @@ static int prepare_plan(frx_ctx* ctx, long long N, const double* d_sampling, boo
                                  ctx->raw_hw.p, ctx->obs.p, st);
         CK(cudaGetLastError());
         ctx->Tp = Tp;
+        ctx->compact_Nt = 0;
+    }
+    if (ctx->O > 0 && ctx->compact_Nt != Nt) {        // per-step compact records (depend on the horizon through min(Nt, len))
+        const int Tp = ctx->Tp;
+        CK(ctx->opred.reserve((size_t)Tp * ctx->O * 8)); CK(ctx->ohull.reserve((size_t)Tp * ctx->O * 8));
+        CK(ctx->on_pred.reserve(Tp)); CK(ctx->on_hull.reserve(Tp));
+        frx_launch_obstacle_compact(ctx->O, Tp, Nt, ctx->obs.p, ctx->obs_len.p, ctx->opred.p, ctx->ohull.p, ctx->on_pred.p,
+                                    ctx->on_hull.p, st);
+        CK(cudaGetLastError());
+        ctx->compact_Nt = Nt;
     }
     const int seg = (seg_hint > 0) ? seg_hint : frx_pick_seg(N, ctx->sm_count);
     const long long n_tiles = (N + 32 / seg - 1) / (32 / seg);     // one warp per tile of 32 / seg rows
@@ -330,6 +345,7 @@ static int prepare_plan(frx_ctx* ctx, long long N, const double* d_sampling, boo
     a.ref = ctx->ref.p; a.M = ctx->M; a.Mpad = ctx->Mpad;
     a.Ttab = ctx->Ttab.p; a.Tlen = ctx->Tlen.p; a.tpow = ctx->tpow.p; a.nT = ctx->nT; a.tpitch = ctx->tpitch;
     a.obs = ctx->obs.p; a.obs_len = ctx->obs_len.p; a.O = ctx->O; a.Tp = ctx->Tp;
+    a.opred = ctx->opred.p; a.ohull = ctx->ohull.p; a.on_pred = ctx->on_pred.p; a.on_hull = ctx->on_hull.p;
     a.obs_pos = ctx->obs_pos.p; a.n_obs_pos = ctx->n_obs_pos; a.sobb = ctx->sobb.p; a.B = ctx->B;
     a.sampling = grid_mode ? nullptr : d_sampling;
     a.g_t1 = d_t1; a.g_v1 = d_v1; a.g_d1 = d_d1; a.g_nv = g_nv; a.g_nd = g_nd;
@@ -429,10 +445,26 @@ static int run_plan(frx_ctx* ctx, long long N, const double* d_sampling, bool gr
     return wait_plan(ctx, out);
 }
 
+// Pinned (page-locked, mapped) host memory is read by the eval kernel in place: every warp prefetches the rows of its
+// next tile over PCIe while it evaluates the current one, there is no staging copy.  FRX_ZEROCOPY=0 disables this.
+static const double* zero_copy_pointer(const double* host) {
+    static int enabled = -1;
+    if (enabled < 0) { const char* e = getenv("FRX_ZEROCOPY"); enabled = (e && e[0] == '0') ? 0 : 1; }
+    if (!enabled) return nullptr;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (at.type != cudaMemoryTypeHost || at.devicePointer == nullptr) return nullptr;
+    return (const double*)at.devicePointer;
+}
+
 int frx_plan(frx_ctx* ctx, int64_t N, const double* sampling, int64_t row_index_base, frx_result* out) {
     if (!ctx) return FRX_ERR_INVALID;
     REQUIRE(N >= 1 && sampling != nullptr, "frx_plan: empty sampling matrix");
     CK(cudaSetDevice(ctx->device));
+    if (const double* mapped = zero_copy_pointer(sampling)) {
+        CK(cudaEventRecord(ctx->ev0, ctx->stream));
+        return run_plan(ctx, N, mapped, false, 0, 0, nullptr, nullptr, nullptr, nullptr, 0, row_index_base, out);
+    }
     CK(ctx->sampling.reserve((size_t)N * 13));
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
     CK(cudaMemcpyAsync(ctx->sampling.p, sampling, (size_t)N * 13 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
@@ -564,6 +596,22 @@ int frx_get_states(frx_ctx* ctx, int64_t n_idx, const int64_t* idx, uint32_t fie
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(out, ctx->gout.p, n_out * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    return FRX_OK;
+}
+
+int frx_winner_states(frx_ctx* ctx, uint32_t field_mask, double* out) {
+    if (!ctx) return FRX_ERR_INVALID;
+    REQUIRE(ctx->lastN > 0 && ctx->last_all_fields, "frx_winner_states: no materialised states (store_states = 0 or no plan yet)");
+    REQUIRE(!ctx->pending, "frx_winner_states: a plan is still in flight (frx_plan_wait first)");
+    REQUIRE(out && field_mask && field_mask < (1u << FRX_NUM_FIELDS), "frx_winner_states: bad arguments");
+    REQUIRE(ctx->h_res->winner.idx >= 0, "frx_winner_states: the last plan selected no candidate");
+    const int pitch = ctx->lastNtp, Nt = ctx->lastNt;
+    int fo = 0;
+    for (int f = 0; f < FRX_NUM_FIELDS; ++f) {
+        if (!(field_mask & (1u << f))) continue;
+        for (int i = 0; i < pitch; ++i) out[(size_t)fo * pitch + i] = (i < Nt) ? ctx->h_res->winner_states[f][i] : 0.0;
+        ++fo;
+    }
     return FRX_OK;
 }
 

@@ -49,6 +49,7 @@ struct FrxBest {
 struct FrxHostResult {
     FrxBest winner;
     unsigned long long counters[FRX_NUM_COUNTERS];
+    double winner_states[FRX_NUM_FIELDS][64];   // the selected candidate's state rows (Nt <= 64 samples each)
 };
 
 struct FrxKernelArgs {
@@ -72,6 +73,10 @@ struct FrxKernelArgs {
     // ---- predictions / obstacles
     const double* obs;      // [O][FRX_OBS_NARR][Tp]
     const int* obs_len;     // [O] valid steps
+    const double* opred;    // [Tp][O][8] per-step compact prediction records (frx_obstacle_compact_kernel)
+    const double* ohull;    // [Tp][O][8] per-step compact hull records
+    const int* on_pred;     // [Tp] records per step
+    const int* on_hull;     // [Tp]
     int O, Tp;
     const double* obs_pos;  // [n_obs_pos][2] current obstacle positions (distance_to_obstacles)
     int n_obs_pos;

@@ -26,6 +26,9 @@
 //
 // Arithmetic follows reactive_planner.py:274-577 of the reference op for op (comments next to each block).
 #pragma once
+#ifndef FRX_OPT_OBS_PREFETCH
+#define FRX_OPT_OBS_PREFETCH 0     // measured: prefetching the next step's obstacle records into L1 changes nothing
+#endif
 
 enum { M_S = 0, M_SD, M_SDD, M_INTERP, M_KR, M_KRD, M_PX, M_PY, M_SN, M_CS, M_T1, M_T2, M_T3, M_T4, M_T5, M_FIELDS };
 
@@ -39,7 +42,8 @@ struct FrxMemoHdr {        // one per memo slot (shared memory)
 
 __host__ __device__ inline size_t frx_tile_smem_bytes(int Mpad, int tpitch) {
     return (size_t)(6 * Mpad + FRX_MAX_T_VALUES + FRX_WARPS_PER_CTA * FRX_MEMO_SLOTS * M_FIELDS * tpitch) * sizeof(double) +
-           FRX_WARPS_PER_CTA * FRX_MEMO_SLOTS * sizeof(FrxMemoHdr) + 16 + FRX_WARPS_PER_CTA * sizeof(FrxBest);
+           FRX_WARPS_PER_CTA * FRX_MEMO_SLOTS * sizeof(FrxMemoHdr) + 16 + FRX_WARPS_PER_CTA * sizeof(FrxBest) +
+           (size_t)FRX_WARPS_PER_CTA * 32 * 13 * sizeof(double);
 }
 
 // Simpson-rule accumulator (scipy simps, dx = dt; partial_cost_functions.py:24-46, :141-151, :189-196), fed one
@@ -488,7 +492,6 @@ __device__ __forceinline__ FrxLaneOut frx_candidate(const FrxKernelArgs& A, cons
         const bool need_d2o = XCOST && costed && (cost_mask & (1u << FRX_COST_DISTANCE_TO_OBSTACLES)) && A.n_obs_pos > 0;
         const bool need_col = OBS && candidate && A.check_collisions && (A.O > 0 || A.B > 0);
         if (need_pred || need_d2o || need_col) {
-            const int OTP = A.Tp;       // step pitch of the obstacle table
             double pbx = 0, pby = 0, pux = 0, puy = 0;   // ego box of the previous step
             if (SEG > 1 && need_col && i0 >= 1 && i0 < i1) {      // ... which another lane wrote for a later segment
                 const double* qp = sp + (size_t)(i0 - 1) * (size_t)Np;
@@ -496,19 +499,64 @@ __device__ __forceinline__ FrxLaneOut frx_candidate(const FrxKernelArgs& A, cons
                 sincos(__ldcg(qp + 2 * fstride), &sn, &cs);
                 pbx = __ldcg(qp) + A.wb_rear * cs; pby = __ldcg(qp + fstride) + A.wb_rear * sn; pux = cs; puy = sn;
             }
+            // x, y, theta of the candidate come back from the state tensor (L2), loaded ONE STEP AHEAD of their use
             const double* q = sp + (size_t)i0 * (size_t)Np;
+            double x_n = 0.0, y_n = 0.0, th_n = 0.0;
+            if (i0 < i1) { x_n = __ldcg(q); y_n = __ldcg(q + fstride); if (need_col) th_n = __ldcg(q + 2 * fstride); }
             for (int i = i0; i < i1; ++i, q += Np) {
-                const double x = __ldcg(q), y = __ldcg(q + fstride);
+                const double x = x_n, y = y_n, th = th_n;
+                if (i + 1 < i1) {
+                    x_n = __ldcg(q + Np); y_n = __ldcg(q + Np + fstride);
+                    if (need_col) th_n = __ldcg(q + Np + 2 * fstride);
+                }
+#if FRX_OPT_OBS_PREFETCH
+                // the records of the NEXT step go to L1 now (warp-uniform addresses: one request per 128-byte line), so
+                // the loops of the next iteration hit L1 instead of waiting for L2 on every group of loads
+                if (OBS && i + 1 < i1) {
+                    if (need_pred) {
+                        const char* pf = reinterpret_cast<const char*>(A.opred + (size_t)i * A.O * 8);
+                        const int nb = __ldg(A.on_pred + i) * 64;
+                        for (int b = 0; b < nb; b += 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(pf + b));
+                    }
+                    if (need_col && i >= 1) {
+                        const char* pf = reinterpret_cast<const char*>(A.ohull + (size_t)(i - 1) * A.O * 8);
+                        const int nb = __ldg(A.on_hull + (i - 1)) * 64;
+                        for (int b = 0; b < nb; b += 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(pf + b));
+                    }
+                }
+#endif
                 if (need_pred && i >= 1) {
-                    for (int o = 0; o < A.O; ++o) {
-                        if (i >= __ldg(A.obs_len + o)) continue;
-                        const double* __restrict__ ob = A.obs + (size_t)o * (FRX_OBS_NARR * OTP) + (i - 1);
-                        double ex = x - __ldg(ob + OB_PX * OTP);
-                        double ey = y - __ldg(ob + OB_PY * OTP);
-                        double t0 = ex * __ldg(ob + OB_IV00 * OTP) + ey * __ldg(ob + OB_IV10 * OTP);
-                        double t1 = ex * __ldg(ob + OB_IV01 * OTP) + ey * __ldg(ob + OB_IV11 * OTP);
+                    // the obstacles predicted at this step: 64-byte records, warp-uniform 16-byte loads
+                    const int n = __ldg(A.on_pred + (i - 1));
+                    const double2* __restrict__ rec = reinterpret_cast<const double2*>(A.opred + (size_t)(i - 1) * A.O * 8);
+                    // branch-free body (loads of the unrolled records issue together, the reciprocal chains overlap);
+                    // an operand outside the fast reciprocal's range (0, inf, nan, denormal: the ego ON an obstacle
+                    // mean) is only recorded -- the step is then redone with IEEE division
+                    const double saved = pred_sum;
+                    bool ok = true;
+#pragma unroll 4
+                    for (int o = 0; o < n; ++o) {
+                        const double2 pp = __ldg(rec + 4 * o), va = __ldg(rec + 4 * o + 1), vb = __ldg(rec + 4 * o + 2);   // (px,py) (iv00,iv10) (iv01,iv11)
+                        double ex = x - pp.x;
+                        double ey = y - pp.y;
+                        double t0 = ex * va.x + ey * va.y;
+                        double t1 = ex * vb.x + ey * vb.y;
                         double m = t0 * ex + t1 * ey;
-                        pred_sum += drcpg(m * m);
+                        double m2 = m * m;
+                        ok = ok && drcp_in_range(m2);
+                        pred_sum += drcp_unchecked(m2);
+                    }
+                    if (!ok) {
+                        pred_sum = saved;
+                        for (int o = 0; o < n; ++o) {
+                            const double2 pp = __ldg(rec + 4 * o), va = __ldg(rec + 4 * o + 1), vb = __ldg(rec + 4 * o + 2);
+                            double ex = x - pp.x;
+                            double ey = y - pp.y;
+                            double t0 = ex * va.x + ey * va.y;
+                            double t1 = ex * vb.x + ey * vb.y;
+                            double m = t0 * ex + t1 * ey;
+                            pred_sum += drcpg(m * m);
+                        }
                     }
                 }
                 if (need_d2o) {
@@ -520,25 +568,37 @@ __device__ __forceinline__ FrxLaneOut frx_candidate(const FrxKernelArgs& A, cons
                 }
                 if (need_col) {
                     double sn, cs;
-                    sincos(__ldcg(q + 2 * fstride), &sn, &cs);
+                    sincos(th, &sn, &cs);
                     const double bx = x + A.wb_rear * cs, by = y + A.wb_rear * sn;     // state.py:30-39 rear axle -> centre
                     if (i >= 1 && !(collide && (boundary || A.B == 0))) {
                         const int k = i - 1;                                            // hull of boxes k, k + 1
                         Hull e = obb_sum_hull(pbx, pby, pux, puy, bx, by, cs, sn, A.half_len, A.half_wid);
                         const double er = sqrt(e.ha * e.ha + e.hb * e.hb) * (1.0 + 1e-9);
                         if (k >= 1 && !collide) {
-                            for (int o = 0; o < A.O; ++o) {
-                                const int len = min(Nt, __ldg(A.obs_len + o));
-                                if (len <= 2 || k > len - 1) continue;
-                                const double* __restrict__ ob = A.obs + (size_t)o * (FRX_OBS_NARR * OTP) + (k - 1);
-                                double ocx = __ldg(ob + OB_HCX * OTP), ocy = __ldg(ob + OB_HCY * OTP);
-                                double rr = er + __ldg(ob + OB_HR * OTP);
-                                double ddx = ocx - e.cx, ddy = ocy - e.cy;
-                                if (ddx * ddx + ddy * ddy > rr * rr) continue;      // conservative broad phase
-                                if (obb_overlap(e, ocx, ocy, __ldg(ob + OB_HUX * OTP), __ldg(ob + OB_HUY * OTP),
-                                                __ldg(ob + OB_HHA * OTP), __ldg(ob + OB_HHB * OTP))) {
-                                    collide = true;
-                                    break;
+                            // obstacle hulls of step k - 1 (hull record: cx, cy, r | ux, uy | ha, hb)
+                            const int n = __ldg(A.on_hull + (k - 1));
+                            const double2* __restrict__ rec = reinterpret_cast<const double2*>(A.ohull + (size_t)(k - 1) * A.O * 8);
+                            // conservative broad phase over all hulls of the step, branch-free (bounding circles, 32
+                            // hulls per mask word); the exact separating-axis test runs for the few that pass
+                            for (int o0 = 0; o0 < n && !collide; o0 += 32) {
+                                const int nn = (n - o0 < 32) ? (n - o0) : 32;
+                                unsigned near_mask = 0;
+#pragma unroll 4
+                                for (int o = 0; o < nn; ++o) {
+                                    const double2 cc = __ldg(rec + 4 * (o0 + o));
+                                    const double hr = __ldg(reinterpret_cast<const double*>(rec + 4 * (o0 + o) + 1));
+                                    double rr = er + hr;
+                                    double ddx = cc.x - e.cx, ddy = cc.y - e.cy;
+                                    near_mask |= (ddx * ddx + ddy * ddy > rr * rr) ? 0u : (1u << o);
+                                }
+                                while (near_mask) {
+                                    const int o = o0 + __ffs(near_mask) - 1;
+                                    near_mask &= near_mask - 1;
+                                    const double2 cc = __ldg(rec + 4 * o), ru = __ldg(rec + 4 * o + 1), uh = __ldg(rec + 4 * o + 2);
+                                    if (obb_overlap(e, cc.x, cc.y, ru.y, uh.x, uh.y, __ldg(reinterpret_cast<const double*>(rec + 4 * o + 3)))) {
+                                        collide = true;
+                                        break;
+                                    }
                                 }
                             }
                         }
@@ -651,6 +711,7 @@ __device__ __forceinline__ void frx_tile_body(const FrxKernelArgs& A, const int 
     FrxMemoHdr* s_hdr = reinterpret_cast<FrxMemoHdr*>(s_memo + (size_t)FRX_WARPS_PER_CTA * FRX_MEMO_SLOTS * M_FIELDS * TP);
     unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_hdr + FRX_WARPS_PER_CTA * FRX_MEMO_SLOTS);
     FrxBest* s_best = reinterpret_cast<FrxBest*>(s_bar + 2);                 // [WARPS]
+    double* s_rows = reinterpret_cast<double*>(s_best + FRX_WARPS_PER_CTA);  // [WARPS][32 * 13] sampling rows of a tile
 
     // ---- stage the reference tables with one TMA bulk copy (UBLKCP) guarded by an mbarrier
     const uint32_t ref_bytes = (uint32_t)(6 * Mpad * sizeof(double));
@@ -678,10 +739,28 @@ __device__ __forceinline__ void frx_tile_body(const FrxKernelArgs& A, const int 
     constexpr int C = 32 / SEG;
     const long long n_tiles = (N + C - 1) / C;
 
-    // Work distribution: warps pull tiles of C consecutive rows from a global ticket counter; the ticket of the
-    // NEXT tile is requested one tile ahead so its latency is hidden.
+    // Work distribution: the first tile of a warp is its global index, further tiles of C consecutive rows come
+    // from a global ticket counter, requested one tile ahead.  The 13-column rows of a tile are one contiguous span
+    // of the sampling matrix: the warp copies it with coalesced 8-byte cp.async into its staging buffer -- the NEXT
+    // tile's rows while the current tile is evaluated, so neither HBM nor (for a pinned host matrix the kernel reads
+    // in place, zero-copy) PCIe latency is ever waited on.
+    const double* __restrict__ samp = A.sampling;
+    double* rows = s_rows + wib * (32 * 13);
+    const long long total_warps = (long long)A.n_cta * FRX_WARPS_PER_CTA;
+    auto stage_rows = [&](long long tile) {
+        const long long base = tile * (C * 13), lim = N * 13;
+#pragma unroll
+        for (int k = 0; k < (C * 13 + 31) / 32; ++k) {
+            const int e = k * 32 + lane;
+            if (e < C * 13 && base + e < lim)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(rows + e)), "l"(samp + base + e) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    long long cur_tile = (long long)cta_local * FRX_WARPS_PER_CTA + wib;
+    if (samp != nullptr && cur_tile < n_tiles) stage_rows(cur_tile);
     unsigned long long next_tile = 0;
-    if (lane == 0) next_tile = atomicAdd(A.counters + CNT_WORK, 1ULL);
+    if (lane == 0) next_tile = atomicAdd(A.counters + CNT_WORK, 1ULL) + (unsigned long long)total_warps;
 
     {   // wait for the bulk copy (phase 0)
         uint32_t done = 0;
@@ -703,20 +782,25 @@ __device__ __forceinline__ void frx_tile_body(const FrxKernelArgs& A, const int 
     unsigned int t_missing = 0;
 
     for (;;) {
-        const long long tile = (long long)__shfl_sync(FULL, next_tile, 0);
+        const long long tile = cur_tile;
         if (tile >= n_tiles) break;
-        if (lane == 0) next_tile = atomicAdd(A.counters + CNT_WORK, 1ULL);
         const long long r = tile * C + (lane & (C - 1));
         const bool in_range = r < N;
         const long long rl = in_range ? r : (N - 1);
         // ---------------- sampling row (sampling_matrix.py:85-121 column order)
         double T, s0, ss0, sss0, ss1, d0, dd0, ddd0, d1, dd1, ddd1;
-        if (A.sampling != nullptr) {
-            const double* __restrict__ row = A.sampling + rl * 13;
-            T = __ldg(row + 1); s0 = __ldg(row + 2); ss0 = __ldg(row + 3); sss0 = __ldg(row + 4); ss1 = __ldg(row + 5);
-            d0 = __ldg(row + 7); dd0 = __ldg(row + 8); ddd0 = __ldg(row + 9); d1 = __ldg(row + 10); dd1 = __ldg(row + 11);
-            ddd1 = __ldg(row + 12);
-        } else {
+        if (samp != nullptr) {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncwarp();
+            const double* row = rows + (int)(rl - tile * C) * 13;
+            T = row[1]; s0 = row[2]; ss0 = row[3]; sss0 = row[4]; ss1 = row[5];
+            d0 = row[7]; dd0 = row[8]; ddd0 = row[9]; d1 = row[10]; dd1 = row[11]; ddd1 = row[12];
+            __syncwarp();
+        }
+        cur_tile = (long long)__shfl_sync(FULL, next_tile, 0);
+        if (samp != nullptr && cur_tile < n_tiles) stage_rows(cur_tile);       // prefetch the next tile's rows
+        if (lane == 0) next_tile = atomicAdd(A.counters + CNT_WORK, 1ULL) + (unsigned long long)total_warps;
+        if (samp == nullptr) {
             const long long g = A.row_first + rl;
             const long long per_t = (long long)A.g_nv * A.g_nd;
             const int it = (int)(g / per_t);
@@ -842,9 +926,22 @@ __device__ __forceinline__ void frx_tile_body(const FrxKernelArgs& A, const int 
                 FrxBest o = s_best[w];
                 if (o.idx >= 0 && (b.idx < 0 || o.cost < b.cost || (o.cost == b.cost && o.idx < b.idx))) b = o;
             }
+            s_best[0] = b;                          // local row, for the state copy below
             if (b.idx >= 0) b.idx += A.row_base;   // the winner record carries the GLOBAL row index
             *A.winner = b;
             A.host_res->winner = b;
+        }
+        __syncthreads();
+        {   // the selected trajectory's 14 state rows go into the mapped result record as well: the host reads the
+            // optimal trajectory without a second round trip
+            const long long wi = s_best[0].idx;
+            if (wi >= 0 && A.store_states) {
+                const int Nt = A.Nt;
+                for (int q = threadIdx.x; q < FRX_NUM_FIELDS * Nt; q += FRX_THREADS) {
+                    const int f = q / Nt, i = q - f * Nt;
+                    A.host_res->winner_states[f][i] = __ldcg(A.states + ((size_t)f * Nt + i) * (size_t)A.Np + wi);
+                }
+            }
         }
         if (threadIdx.x < FRX_NUM_COUNTERS) {
             unsigned long long v = atomicExch(A.counters + threadIdx.x, 0ULL);   // snapshot + reset in one step

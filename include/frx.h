@@ -173,6 +173,11 @@ int frx_get_states(frx_ctx* ctx, int64_t n_idx, const int64_t* idx, uint32_t fie
 int frx_get_states_range(frx_ctx* ctx, int64_t first, int64_t count, uint32_t field_mask, double* out);
 int frx_get_costs(frx_ctx* ctx, int64_t first, int64_t count, double* costs, double* total);
 int frx_get_flags(frx_ctx* ctx, int64_t first, int64_t count, uint32_t* flags, int32_t* traj_len);
+/* state rows of the selected candidate (frx_result.argmin) of the last plan: out[n_fields][frx_state_pitch()].
+ * The eval kernel's last CTA writes them into the mapped result record together with the arg-min, so this is a
+ * host-side copy -- no device round trip (reference: the optimal trajectory handed back by plan(),
+ * frenetix_motion_planner/reactive_planner.py:89-94) */
+int frx_winner_states(frx_ctx* ctx, uint32_t field_mask, double* out);
 /* raw device pointers of the last plan (states, costs, total, flags) for zero-copy consumers */
 int frx_device_pointers(frx_ctx* ctx, void** states, void** costs, void** total, void** flags);
 /* device address of the 16-byte winner record {double min_cost; int64 global_row} of the last plan:

@@ -71,3 +71,41 @@ def test_division_by_plan_constants_is_ieee_exact():
         q1, q2 = h.selftest_divc(a, b)
         assert (q1 == q2).all(), f"b={b}: {(q1 != q2).sum()} mismatches"
         assert (q1 == a / b).all()
+
+
+@pytest.mark.parametrize("name", ["arc_hv_draw_pred", "scurve_brake_hv_nodraw_nodebug"])
+def test_winner_states_record_equals_gathered_row(name):
+    """The selected trajectory published with the arg-min (mapped result record) is the gathered state row."""
+    g, ref, prm, preds = load_golden(name)
+    dev = device_plan(g["sampling"], ref, prm, preds)
+    h = dev["handler"]
+    assert dev["argmin"] >= 0
+    w = h.winner_states()
+    ref_rows = h.get_states(np.array([dev["argmin"]], dtype=np.int64))[:, 0, :]
+    assert w.shape == ref_rows.shape
+    assert np.array_equal(w, ref_rows)
+    assert np.array_equal(w, dev["states"][:, dev["argmin"], :])
+
+
+def test_pinned_host_matrix_is_read_in_place():
+    """A pinned sampling matrix takes the zero-copy path (kernel prefetches rows over PCIe); same result bit for bit."""
+    import torch
+    from frenetix_motion_planner_b200 import _capi
+    from helpers import configure_handler
+    g, ref, prm, preds = load_golden("arc_hv_draw_pred")
+    S = np.ascontiguousarray(np.tile(g["sampling"], (7, 1))[:5003])      # ragged last tile, several tiles per warp
+    dev = device_plan(S, ref, prm, preds)
+    h = _capi.Handler(0)
+    configure_handler(h, ref, prm, preds, None, sampling=S)
+    Sp = torch.from_numpy(S.copy()).pin_memory()
+    res = h.plan(Sp.numpy())
+    assert int(res.argmin) == dev["argmin"] and float(res.min_cost) == dev["min_cost"]
+    flags, traj_len = h.get_flags()
+    costs, total = h.get_costs()
+    assert np.array_equal(flags, dev["flags"]) and np.array_equal(traj_len, dev["traj_len"])
+    assert np.array_equal(total, dev["total"]) and np.array_equal(costs, dev["costs"])
+    assert np.array_equal(h.get_states_range(), dev["states"])
+    # an unaligned view into the pinned buffer (row offset, 8-byte alignment only) works as well
+    res2 = h.plan(Sp.numpy()[3:])
+    d2 = device_plan(S[3:], ref, prm, preds)
+    assert int(res2.argmin) == d2["argmin"] and float(res2.min_cost) == d2["min_cost"]
