@@ -527,8 +527,9 @@ def main():
                     "d2h_bytes_per_step": int(16 + 8 * 17 + 14 * 32 * 8),
                     "ms_per_step": 1e3 * e2e_s / args.steps, "eval_kernel_ms": float(np.mean(e2e_kern_ms)),
                     "device_ms": float(np.mean(e2e_dev_ms)),
-                    "note": "frx_plan on a PINNED HOST sampling matrix: the eval kernel reads the rows in place over PCIe "
-                            "(cp.async prefetch one tile ahead, no staging copy; FRX_ZEROCOPY=0 restores cudaMemcpyAsync), "
+                    "note": ("frx_plan_grid on HOST axes t1/ss1/d1 + x_cl (rows expanded on the device); " if grid_mode else
+                             "frx_plan on a PINNED HOST sampling matrix: the eval kernel reads the rows in place over PCIe "
+                             "(cp.async prefetch one tile ahead, no staging copy; FRX_ZEROCOPY=0 restores cudaMemcpyAsync); ") +
                             "the result record and the selected trajectory's 14 state rows come back through mapped host "
                             "memory written by the kernel's last CTA; wall clock around the C-ABI call"},
             "gpu_launches": gpu_launches, "clocks": clocks,
