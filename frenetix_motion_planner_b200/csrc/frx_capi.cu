@@ -23,7 +23,6 @@ void frx_launch_obstacle_prep(int O, int T, int Tp, const double* pos, const dou
 void frx_launch_static_prep(int B, const double* obb, double* out, cudaStream_t st);
 void frx_launch_obstacle_compact(int O, int Tp, int Nt, const double* obs, const int* obs_len, double* pred, double* hull,
                                  int* n_pred, int* n_hull, cudaStream_t st);
-void frx_launch_argmin(const FrxBest* bb, int nblocks, long long row_base, FrxBest* out, cudaStream_t st);
 void frx_launch_collision_counter(long long N, long long row_base, const double* total, const uint32_t* flags,
                                   const FrxBest* winner, unsigned long long* counters, int grid, cudaStream_t st);
 void frx_launch_gather(const double* states, long long Np, int Nt, int Ntp, const long long* idx, long long first,

@@ -26,6 +26,9 @@
 //
 // Arithmetic follows reactive_planner.py:274-577 of the reference op for op (comments next to each block).
 #pragma once
+#ifndef FRX_STEP_UNROLL
+#define FRX_STEP_UNROLL 1
+#endif
 #ifndef FRX_OPT_OBS_PREFETCH
 #define FRX_OPT_OBS_PREFETCH 0     // measured: prefetching the next step's obstacle records into L1 changes nothing
 #endif
@@ -299,6 +302,8 @@ __device__ __forceinline__ FrxLaneOut frx_candidate(const FrxKernelArgs& A, cons
     const int nA = Nt, nbA = (nA & 1) ? nA : (nA - 1);            // integrands sampled at every step
     const int nD = Nt - 1, nbD = (nD & 1) ? nD : (nD - 1);        // integrands built from np.diff
 
+    constexpr int kStepUnroll = FRX_STEP_UNROLL;
+#pragma unroll kStepUnroll
     for (int i = i0; i < i1; ++i) {
         const double si = mt[M_S * TP + i], sdi = mt[M_SD * TP + i], sddi = mt[M_SDD * TP + i];
         double di = 0, ddi = 0, dddi = 0;

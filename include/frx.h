@@ -61,7 +61,9 @@ extern "C" {
 #define FRX_ERR_NOMEM (-3)
 #define FRX_ERR_UNSUPPORTED (-4)
 
-/* state tensor fields: states[field][candidate][step], step pitch = frx_state_pitch() */
+/* state tensor fields.  Read-back (frx_get_states*, frx_winner_states) delivers out[field][candidate][step] with step
+ * pitch frx_state_pitch(); in HBM the tensor is laid out [field][step][candidate] (candidate fastest, padded to a
+ * multiple of 32) so that the 32 candidates of a warp store 256 contiguous bytes per field and step. */
 enum {
     FRX_F_X = 0, FRX_F_Y, FRX_F_THETA, FRX_F_V, FRX_F_A, FRX_F_KAPPA, FRX_F_KAPPA_DOT,
     FRX_F_S, FRX_F_D, FRX_F_THETA_CL, FRX_F_S_DOT, FRX_F_S_DDOT, FRX_F_D_DOT, FRX_F_D_DDOT,
@@ -101,7 +103,7 @@ typedef struct frx_params {
     int32_t n_costs;                       /* active cost terms, name-sorted */
     int32_t cost_ids[FRX_MAX_COSTS];       /* FRX_COST_* */
     double cost_weights[FRX_MAX_COSTS];
-    int32_t store_states;    /* 1: materialise states[14][N][pitch] in HBM (default) */
+    int32_t store_states;    /* 1: materialise the 14 state planes [14][Nt][N] in HBM (default) */
     int32_t check_collisions;/* 1: OBB sweep vs predictions / static boxes for every candidate */
 } frx_params;
 
@@ -143,7 +145,9 @@ int frx_set_obstacle_positions(frx_ctx* ctx, int32_t n, const double* pos_xy);
 int frx_set_static_obbs(frx_ctx* ctx, int32_t B, const double* obb);
 
 /* rows: host [N][13] = t0,t1,s0,ss0,sss0,ss1,sss1,d0,dd0,ddd0,d1,dd1,ddd1.  row_index_base is
- * added to local row numbers in frx_result.argmin (shards of a larger matrix). */
+ * added to local row numbers in frx_result.argmin (shards of a larger matrix).  A pageable matrix is staged with
+ * one cudaMemcpyAsync; a pinned (page-locked) one is read by the eval kernel in place -- every warp prefetches the
+ * rows of its next tile over PCIe while it evaluates the current one (FRX_ZEROCOPY=0 forces the staged copy). */
 int frx_plan(frx_ctx* ctx, int64_t N, const double* sampling, int64_t row_index_base, frx_result* out);
 /* same, sampling already in device memory (pointer from cudaMalloc / torch) */
 int frx_plan_device(frx_ctx* ctx, int64_t N, const void* d_sampling, int64_t row_index_base,
@@ -178,7 +182,8 @@ int frx_get_flags(frx_ctx* ctx, int64_t first, int64_t count, uint32_t* flags, i
  * host-side copy -- no device round trip (reference: the optimal trajectory handed back by plan(),
  * frenetix_motion_planner/reactive_planner.py:89-94) */
 int frx_winner_states(frx_ctx* ctx, uint32_t field_mask, double* out);
-/* raw device pointers of the last plan (states, costs, total, flags) for zero-copy consumers */
+/* raw device pointers of the last plan for zero-copy consumers: states [14][Nt][Np] (Np = N rounded up to 32),
+ * costs [N][n_costs], total [N], flags [N] */
 int frx_device_pointers(frx_ctx* ctx, void** states, void** costs, void** total, void** flags);
 /* device address of the 16-byte winner record {double min_cost; int64 global_row} of the last plan:
  * the payload of the multi-GPU arg-min exchange (all-gather of 16 B per rank, no host round trip) */
