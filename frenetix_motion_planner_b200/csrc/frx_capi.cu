@@ -1,6 +1,7 @@
 // frx_capi.cu -- the C ABI (include/frx.h) over the sm_100a kernels.  Host C++ only; no torch types.
 #include <cuda_runtime.h>
 #include <stdlib.h>
+#include <stdio.h>
 #include <math.h>
 #include <stdint.h>
 #include <string.h>
@@ -74,6 +75,7 @@ struct frx_ctx {
     DevBuf<double> sobb, raw_sobb; int B = 0;
     DevBuf<double> sampling, grid;
     DevBuf<double> states, costs, total; DevBuf<uint32_t> flags; DevBuf<int> traj_len;
+    DevBuf<unsigned long long> blockcnt;
     DevBuf<FrxBest> blockbest, winner; DevBuf<unsigned long long> counters;
     DevBuf<long long> gidx; DevBuf<double> gout;
     DevBuf<FrxKernelArgs> batch_args; DevBuf<int> batch_cta;
@@ -152,7 +154,7 @@ int frx_destroy(frx_ctx* ctx) {
     ctx->raw_hl.release(); ctx->raw_hw.release(); ctx->obs_len.release(); ctx->obs_pos.release();
     ctx->sobb.release(); ctx->raw_sobb.release(); ctx->sampling.release(); ctx->grid.release();
     ctx->states.release(); ctx->costs.release(); ctx->total.release(); ctx->flags.release(); ctx->traj_len.release();
-    ctx->blockbest.release(); ctx->winner.release(); ctx->counters.release(); ctx->gidx.release(); ctx->gout.release(); ctx->batch_args.release(); ctx->batch_cta.release();
+    ctx->blockcnt.release(); ctx->blockbest.release(); ctx->winner.release(); ctx->counters.release(); ctx->gidx.release(); ctx->gout.release(); ctx->batch_args.release(); ctx->batch_cta.release();
     if (ctx->h_res) cudaFreeHost(ctx->h_res);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -327,11 +329,15 @@ static int prepare_plan(frx_ctx* ctx, long long N, const double* d_sampling, boo
     }
     const int seg = (seg_hint > 0) ? seg_hint : frx_pick_seg(N, ctx->sm_count);
     const long long n_tiles = (N + 32 / seg - 1) / (32 / seg);     // one warp per tile of 32 / seg rows
-    long long want = (n_tiles + FRX_WARPS_PER_CTA - 1) / FRX_WARPS_PER_CTA;
+    // All resident CTA slots are used as soon as there is a tile per CTA: first tiles are dealt warp-major (tile =
+    // warp-in-CTA x grid + CTA), so a plan with fewer tiles than warps leaves the idle warps spread evenly over the SMs
+    // instead of filling some SMs with two busy CTAs and others with one.
+    long long want = n_tiles;
     long long full = (max_grid > 0) ? max_grid : (long long)ctx->sm_count * ctx->occ_blocks;
     int grid = (int)(want < full ? want : full);
     if (grid < 1) grid = 1;
     CK(ctx->blockbest.reserve(grid));
+    CK(ctx->blockcnt.reserve((size_t)grid * (CNT_REASON1 + 10)));
 
     FrxKernelArgs a;
     memset(&a, 0, sizeof(a));
@@ -352,7 +358,7 @@ static int prepare_plan(frx_ctx* ctx, long long N, const double* d_sampling, boo
     a.row_first = row_first; a.row_base = row_base; a.N = N;
     a.states = ctx->states.p; a.costs = ctx->costs.p; a.total = ctx->total.p; a.flags = ctx->flags.p;
     a.seg = seg; a.Np = Np; a.keep_xyt = (!p.store_states && need_xyt) ? 1 : 0;
-    a.traj_len = ctx->traj_len.p; a.blockbest = ctx->blockbest.p; a.counters = ctx->counters.p;
+    a.traj_len = ctx->traj_len.p; a.blockbest = ctx->blockbest.p; a.blockcnt = ctx->blockcnt.p; a.counters = ctx->counters.p;
     a.winner = ctx->winner.p; a.host_res = ctx->d_res; a.n_cta = grid;
     if (ctx->counters_dirty) {
         CK(cudaMemsetAsync(ctx->counters.p, 0, sizeof(unsigned long long) * FRX_NUM_COUNTERS, st));
@@ -411,9 +417,26 @@ static int enqueue_plan(frx_ctx* ctx, long long N, const double* d_sampling, boo
                           &a, &grid, &nchunk);
     if (rc != FRX_OK) return rc;
     ctx->counters_dirty = true;          // cleared again once the launch sequence has completed
+#ifdef FRX_TRACE
+    static DevBuf<unsigned long long> trace;
+    const size_t n_tr = (size_t)grid * FRX_WARPS_PER_CTA * 8;
+    CK(trace.reserve(n_tr));
+    CK(cudaMemsetAsync(trace.p, 0, n_tr * 8, st));
+    a.trace = trace.p;
+#endif
     CK(cudaEventRecord(ctx->evk0, st));
     CK(frx_launch_eval(a, nchunk, grid, st));
     CK(cudaEventRecord(ctx->evk1, st));
+#ifdef FRX_TRACE
+    {
+        std::vector<unsigned long long> h(n_tr);
+        CK(cudaMemcpyAsync(h.data(), trace.p, n_tr * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (const char* path = getenv("FRX_TRACE_FILE")) {
+            if (FILE* f = fopen(path, "wb")) { fwrite(h.data(), 8, n_tr, f); fclose(f); }
+        }
+    }
+#endif
     rc = enqueue_finish(ctx, N, row_base, grid, st);
     if (rc != FRX_OK) return rc;
     CK(cudaEventRecord(ctx->ev1, st));

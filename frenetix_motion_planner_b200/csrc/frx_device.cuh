@@ -100,8 +100,10 @@ struct FrxKernelArgs {
     uint32_t* flags;        // [N]
     int* traj_len;          // [N]
     FrxBest* blockbest;     // [n_cta]
+    unsigned long long* blockcnt;   // [n_cta][CNT_REASON1 + 10] per-CTA event counters (summed by the last CTA)
     unsigned long long* counters;
     FrxBest* winner;        // device copy of the winner record (multi-GPU exchange payload)
     FrxHostResult* host_res;// device address of the mapped host result struct
+    unsigned long long* trace;  // FRX_TRACE tuning builds: [warps][8] globaltimer stamps, else null
     int n_cta;              // CTAs working on this plan (grid size, or this agent's share of a batched grid)
 };

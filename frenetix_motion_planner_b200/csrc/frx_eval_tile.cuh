@@ -26,6 +26,23 @@
 //
 // Arithmetic follows reactive_planner.py:274-577 of the reference op for op (comments next to each block).
 #pragma once
+// FRX_TRACE (tuning builds only): every warp records globaltimer stamps of its first tile into A.trace[warp][8]
+#ifndef FRX_TRACE
+#define FRX_TRACE 0
+#endif
+#if FRX_TRACE
+__device__ __forceinline__ unsigned long long frx_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define FRX_STAMP(k) do { if (A.trace && lane == 0 && !traced) A.trace[((size_t)cta_local * FRX_WARPS_PER_CTA + wib) * 8 + (k)] = frx_now(); } while (0)
+#else
+#define FRX_STAMP(k) do { } while (0)
+#endif
+#ifndef FRX_OPT_FASTSTEP
+#define FRX_OPT_FASTSTEP 1
+#endif
 #ifndef FRX_STEP_UNROLL
 #define FRX_STEP_UNROLL 1
 #endif
@@ -305,6 +322,99 @@ __device__ __forceinline__ FrxLaneOut frx_candidate(const FrxKernelArgs& A, cons
     constexpr int kStepUnroll = FRX_STEP_UNROLL;
 #pragma unroll kStepUnroll
     for (int i = i0; i < i1; ++i) {
+#if FRX_OPT_FASTSTEP
+        // ---- the common case as ONE straight-line block (selects, no branches), so that the independent fp64 chains
+        // (the two slope divisions, atan, the reciprocal square root, the 1/qc refinement, the a_max(v) quotient) overlap
+        // instead of running one after the other behind reconvergence points; the rare cases -- stand-still step in
+        // high-velocity mode, a divisor outside the fast reciprocal's range -- are detected and the step is redone by
+        // the exact general code below.  Same operations, same bits in the common case.
+        const double si = mt[M_S * TP + i], sdi = mt[M_SD * TP + i], sddi = mt[M_SDD * TP + i];
+        const double interp = mt[M_INTERP * TP + i];
+        const double k_r = mt[M_KR * TP + i], k_r_d = mt[M_KRD * TP + i];
+        double di, ddi, dddi;
+        {
+            const double q1 = si - s_first, q2 = q1 * q1, q3 = q2 * q1, q4 = q2 * q2, q5 = q4 * q1;
+            const double u1 = low ? q1 : mt[M_T1 * TP + i], u2 = low ? q2 : mt[M_T2 * TP + i], u3 = low ? q3 : mt[M_T3 * TP + i],
+                         u4 = low ? q4 : mt[M_T4 * TP + i], u5 = low ? q5 : mt[M_T5 * TP + i];
+            const bool inpoly = i < traj_len;
+            const double pd = poly_pos(Q, u1, u2, u3, u4, u5), pv = poly_vel(Q, u1, u2, u3, u4), pa = poly_acc(Q, u1, u2, u3);
+            di = inpoly ? pd : d_last; ddi = inpoly ? pv : 0.0; dddi = inpoly ? pa : 0.0;
+        }
+        const bool mov = sdi > 0.001;
+        const bool direct = mov || low;
+        const bool deferred = (SEG > 1) && (i == i0) && (seg > 0);
+        const bool has_prev = (i > 0) && !deferred;
+        double dp, dpp;
+        {
+            const double qa = ddivf(ddi, sdi);
+            const double dph = mov ? qa : 0.;
+            const double ddot = dddi - dph * sddi;
+            const double qb = ddivf(ddot, sdi * sdi);
+            dp = low ? ddi : dph;
+            dpp = low ? dddi : (mov ? qb : 0.);
+        }
+        double th_cl = atan(dp);                     // np.arctan2(dp, 1.0)
+        double th_gl = th_cl + interp;
+        const double oneKrD = 1 - k_r * di;
+        const double w = 1.0 + dp * dp;
+        double cosT = drsqrt_ge1(w), secT = w * cosT, tanT = dp;
+        double qc = oneKrD * secT;
+        double cq = drcp_unchecked(qc);
+        double kappa = (dpp + (k_r * dp + k_r_d * di) * tanT) * cosT * (cq * cq) + cq * k_r;
+        double vi = sdi * qc;
+        double ai = sddi * qc + ((sdi * sdi) * secT) * (oneKrD * tanT * (kappa * qc - k_r) - (k_r_d * di + k_r * dp));
+        const double a_q = ddivf(A.a_max * A.v_switch, vi);
+        double a_hi = (vi > A.v_switch) ? a_q : A.a_max;
+        if (evaluate && (!direct || !drcp_in_range(qc) || ((vi > A.v_switch) && !drcp_in_range(vi)))) {
+            // ---- the general path (:423-478): stand-still keeps the previous global orientation and needs real
+            // trigonometry; degenerate divisors go through IEEE division
+            if (!direct) { th_gl = th_prev; th_cl = th_gl - interp; }
+            if (direct) {
+                cosT = rsqrt(w); secT = w * cosT; tanT = dp;
+            } else {
+                double sT;
+                sincos(th_cl, &sT, &cosT);
+                secT = ddivg(1.0, cosT);
+                tanT = sT * secT;
+            }
+            qc = oneKrD * secT;
+            cq = ddivg(1.0, qc);
+            kappa = (dpp + (k_r * dp + k_r_d * di) * tanT) * cosT * (cq * cq) + cq * k_r;
+            vi = sdi * qc;
+            ai = sddi * qc + ((sdi * sdi) * secT) * (oneKrD * tanT * (kappa * qc - k_r) - (k_r_d * di + k_r * dp));
+            a_hi = (vi > A.v_switch) ? ddivg(A.a_max * A.v_switch, vi) : A.a_max;
+        }
+        // :483-533 gates
+        uint32_t g = 0;
+        {
+            const double yaw_rate = has_prev ? ddivc(th_gl - th_prev, dT, A.inv_dt) : 0.;
+            const double theta_dot_max = A.kappa_max * vi;
+            const double kappa_dot = has_prev ? ddivc(kappa - ka_prev, dT, A.inv_dt) : 0.;
+            g |= (vi < -FRX_EPS) ? 1u : 0u;
+            g |= (fabs(kappa) > A.kappa_max) ? 2u : 0u;
+            g |= (fabs(ddivc(rint(yaw_rate * 100000.0), 100000.0, 1e-5)) > theta_dot_max) ? 4u : 0u;
+            g |= (fabs(kappa_dot) > 0.4) ? 8u : 0u;
+            g |= (!(-A.a_max <= ai && ai <= a_hi)) ? 16u : 0u;
+        }
+        double kd = has_prev ? (kappa - ka_prev) : 0.0;   // np.append([0], np.diff(kappa_gl))
+        // :536-547 Cartesian position: zero from the first out-of-domain step on
+        const bool inside = i < first_none;
+        double xi = inside ? (mt[M_PX * TP + i] - di * mt[M_SN * TP + i]) : 0.0;
+        double yi = inside ? (mt[M_PY * TP + i] + di * mt[M_CS * TP + i]) : 0.0;
+        if (evaluate) {
+            if (deferred) {
+                g_first = g; th_first = th_gl; ka_first = kappa; vi_first = vi; a_first = ai; thc_first = th_cl;
+            } else if (brk) {
+                if (!gate_hit && g) { gate_or = g & (~g + 1u); gate_hit = true; }   // first violating step, its first gate only
+            } else {
+                gate_or |= g;
+            }
+            th_prev = th_gl;
+            ka_prev = kappa;
+        } else {
+            xi = 0.0; yi = 0.0; th_gl = 0.0; th_cl = 0.0; vi = 0.0; ai = 0.0; kappa = 0.0; kd = 0.0;
+        }
+#else
         const double si = mt[M_S * TP + i], sdi = mt[M_SD * TP + i], sddi = mt[M_SDD * TP + i];
         double di = 0, ddi = 0, dddi = 0;
         if (i < traj_len) {
@@ -391,6 +501,7 @@ __device__ __forceinline__ FrxLaneOut frx_candidate(const FrxKernelArgs& A, cons
             th_prev = th_gl;
             ka_prev = kappa;
         }
+#endif
         // running sums of the two default reductions (velocity_offset :120-130, distance_to_reference_path :154-169)
         if (i >= half && i < Nt - 1) vo_sum += fabs(vi - A.v_des);
         dr_sum += fabs(di);
@@ -705,11 +816,16 @@ __device__ __forceinline__ FrxLaneOut frx_candidate(const FrxKernelArgs& A, cons
 // ------------------------------------------------------------------------------------------------------------
 // kernel body: prologue (TMA staging of the reference tables), tile loop, per-CTA / last-CTA arg-min
 // ------------------------------------------------------------------------------------------------------------
+static_assert(FRX_THREADS >= 96, "the last-CTA epilogue assigns roles to threads 0, 32..47 and 64..69");
 template <int SEG, bool OBS, bool XCOST>
 __device__ __forceinline__ void frx_tile_body(const FrxKernelArgs& A, const int cta_local, unsigned char* smem_raw) {
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
     const int Mpad = A.Mpad, TP = A.tpitch;
+#if FRX_TRACE
+    bool traced = false;
+#endif
+    FRX_STAMP(0);                                                            // kernel entry
     double* s_ref = reinterpret_cast<double*>(smem_raw);                    // [6][Mpad]
     double* s_Ttab = s_ref + 6 * Mpad;                                       // [FRX_MAX_T_VALUES]
     double* s_memo = s_Ttab + FRX_MAX_T_VALUES;                              // [WARPS][SLOTS][M_FIELDS][TP]
@@ -737,6 +853,9 @@ __device__ __forceinline__ void frx_tile_body(const FrxKernelArgs& A, const int 
     for (int k = threadIdx.x; k < FRX_MAX_T_VALUES; k += FRX_THREADS)
         s_Ttab[k] = (k < A.nT) ? A.Ttab[k] : __longlong_as_double(0x7ff8000000000000LL);
     if (lane < FRX_MEMO_SLOTS) s_hdr[wib * FRX_MEMO_SLOTS + lane].valid = 0;
+    __shared__ unsigned int s_cnt[CNT_REASON1 + 10];     // per-CTA event counters
+    __shared__ unsigned long long s_part[FRX_THREADS];   // last CTA: partial counter sums
+    if (threadIdx.x < CNT_REASON1 + 10) s_cnt[threadIdx.x] = 0u;
 
     unsigned cost_mask = 0;
     for (int k = 0; k < A.n_costs; ++k) cost_mask |= 1u << A.cost_ids[k];
@@ -762,7 +881,7 @@ __device__ __forceinline__ void frx_tile_body(const FrxKernelArgs& A, const int 
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    long long cur_tile = (long long)cta_local * FRX_WARPS_PER_CTA + wib;
+    long long cur_tile = (long long)wib * A.n_cta + cta_local;      // warp-major: idle warps (few tiles) spread over all CTAs
     if (samp != nullptr && cur_tile < n_tiles) stage_rows(cur_tile);
     unsigned long long next_tile = 0;
     if (lane == 0) next_tile = atomicAdd(A.counters + CNT_WORK, 1ULL) + (unsigned long long)total_warps;
@@ -779,6 +898,7 @@ __device__ __forceinline__ void frx_tile_body(const FrxKernelArgs& A, const int 
     }
     __syncthreads();
 
+    FRX_STAMP(1);                                                            // reference tables staged
     double* memo = s_memo + (size_t)wib * FRX_MEMO_SLOTS * M_FIELDS * TP;
     FrxMemoHdr* hdr = s_hdr + wib * FRX_MEMO_SLOTS;
     double best_cost = __longlong_as_double(0x7ff0000000000000LL);  // +inf
@@ -802,6 +922,7 @@ __device__ __forceinline__ void frx_tile_body(const FrxKernelArgs& A, const int 
             d0 = row[7]; dd0 = row[8]; ddd0 = row[9]; d1 = row[10]; dd1 = row[11]; ddd1 = row[12];
             __syncwarp();
         }
+        FRX_STAMP(2);                                                        // rows of the first tile in registers
         cur_tile = (long long)__shfl_sync(FULL, next_tile, 0);
         if (samp != nullptr && cur_tile < n_tiles) stage_rows(cur_tile);       // prefetch the next tile's rows
         if (lane == 0) next_tile = atomicAdd(A.counters + CNT_WORK, 1ULL) + (unsigned long long)total_warps;
@@ -852,6 +973,7 @@ __device__ __forceinline__ void frx_tile_body(const FrxKernelArgs& A, const int 
                 frx_memo_fill(A, s_ref, s_Ttab, memo + (size_t)sb * M_FIELDS * TP, hdr + sb, bT, bs0, bss0, bsss0, bss1);
             }
             __syncwarp();
+            FRX_STAMP(3);                                                    // memo slots ready
             const unsigned pass = mA | mB;
             FrxLaneOut o;
             o.ev = 0; o.total = 0.0; o.winner_ok = false; o.t_missing = false;
@@ -861,6 +983,7 @@ __device__ __forceinline__ void frx_tile_body(const FrxKernelArgs& A, const int 
                                               hdr + slot);
             }
             __syncwarp();
+            FRX_STAMP(4);                                                    // candidates of the pass evaluated
             // the running arg-min (planner.py:384-392); rows of a lane only grow, so `<` keeps the lowest row
             if (o.winner_ok && o.total < best_cost) { best_cost = o.total; best_idx = r; }
             if (o.t_missing) t_missing++;
@@ -873,6 +996,10 @@ __device__ __forceinline__ void frx_tile_body(const FrxKernelArgs& A, const int 
             }
             todo &= ~pass;
         }
+#if FRX_TRACE
+        FRX_STAMP(5);                                                        // first tile done
+        traced = true;
+#endif
     }
 
     // ---------------- per-warp, per-CTA reduction of (min cost, lowest row) and the counters
@@ -882,14 +1009,23 @@ __device__ __forceinline__ void frx_tile_body(const FrxKernelArgs& A, const int 
         const long long oi = __shfl_xor_sync(FULL, best_idx, off);
         if (oi >= 0 && (best_idx < 0 || oc < best_cost || (oc == best_cost && oi < best_idx))) { best_cost = oc; best_idx = oi; }
     }
+#if FRX_TRACE
+    traced = false;
+#endif
+    FRX_STAMP(6);                                                            // all tiles of this warp done
     t_missing = __reduce_add_sync(FULL, t_missing);
     if (lane == 0) {
         s_best[wib].cost = best_cost;
         s_best[wib].idx = best_idx;
         if (t_missing) atomicAdd(A.counters + CNT_T_NOT_FOUND, (unsigned long long)t_missing);
     }
-    if (lane < CNT_REASON1 + 10 && my_cnt) atomicAdd(A.counters + lane, (unsigned long long)my_cnt);
+    // event counters: summed per CTA in shared memory and written as one row of A.blockcnt (plain stores) -- thousands
+    // of same-address global atomics at the end of the kernel would queue up right in front of the done-counter
+    if (lane < CNT_REASON1 + 10 && my_cnt) atomicAdd(&s_cnt[lane], my_cnt);
     __syncthreads();   // thread 0's fence below is cumulative over what the barrier made visible to it
+    if (threadIdx.x < CNT_REASON1 + 10)
+        A.blockcnt[(size_t)cta_local * (CNT_REASON1 + 10) + threadIdx.x] = s_cnt[threadIdx.x];
+    __syncthreads();
     __shared__ int s_is_last;
     if (threadIdx.x == 0) {
         FrxBest b = s_best[0];
@@ -908,12 +1044,22 @@ __device__ __forceinline__ void frx_tile_body(const FrxKernelArgs& A, const int 
     // mapped host struct (no memcpy node) and re-arms the counters for the next launch
     if (s_is_last) {
         __threadfence();
+        // one round of loads: this thread's share of the per-CTA winners and of the per-CTA counter rows
+        constexpr int NC = CNT_REASON1 + 10;
+        constexpr int NPART = FRX_THREADS / NC;
         FrxBest b; b.cost = __longlong_as_double(0x7ff0000000000000LL); b.idx = -1;
         for (int k = threadIdx.x; k < A.n_cta; k += FRX_THREADS) {
             FrxBest o;
             o.cost = __ldcg(&A.blockbest[k].cost);
             o.idx = __ldcg(&A.blockbest[k].idx);
             if (o.idx >= 0 && (b.idx < 0 || o.cost < b.cost || (o.cost == b.cost && o.idx < b.idx))) b = o;
+        }
+        {   // thread t: counter t % NC, CTAs t / NC, t / NC + NPART, ...
+            const int c = threadIdx.x % NC, part = threadIdx.x / NC;
+            unsigned long long acc = 0;
+            if (part < NPART)
+                for (int k = part; k < A.n_cta; k += NPART) acc += __ldcg(A.blockcnt + (size_t)k * NC + c);
+            s_part[threadIdx.x] = acc;
         }
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
@@ -935,6 +1081,17 @@ __device__ __forceinline__ void frx_tile_body(const FrxKernelArgs& A, const int 
             if (b.idx >= 0) b.idx += A.row_base;   // the winner record carries the GLOBAL row index
             *A.winner = b;
             A.host_res->winner = b;
+        } else if (threadIdx.x >= 32 && threadIdx.x < 32 + NC) {
+            const int c = threadIdx.x - 32;
+            unsigned long long tot = 0;
+            for (int q = 0; q < NPART; ++q) tot += s_part[q * NC + c];
+            A.host_res->counters[c] = tot;
+        } else if (threadIdx.x >= 64 && threadIdx.x < 64 + (FRX_NUM_COUNTERS - NC)) {
+            // the few global counters (collision counter of the previous plan's second kernel, unknown durations,
+            // tickets, done): snapshot + reset in one step
+            const int c = NC + (threadIdx.x - 64);
+            unsigned long long v = atomicExch(A.counters + c, 0ULL);
+            A.host_res->counters[c] = v;
         }
         __syncthreads();
         {   // the selected trajectory's 14 state rows go into the mapped result record as well: the host reads the
@@ -948,10 +1105,8 @@ __device__ __forceinline__ void frx_tile_body(const FrxKernelArgs& A, const int 
                 }
             }
         }
-        if (threadIdx.x < FRX_NUM_COUNTERS) {
-            unsigned long long v = atomicExch(A.counters + threadIdx.x, 0ULL);   // snapshot + reset in one step
-            A.host_res->counters[threadIdx.x] = v;
-        }
-        __threadfence_system();
+        // no system-scope fence: the host reads the record after synchronising with the stream, and kernel completion
+        // makes every write (mapped host memory included) visible to it
     }
+    FRX_STAMP(7);                                                            // kernel exit
 }

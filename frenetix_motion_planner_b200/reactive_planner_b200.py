@@ -357,6 +357,8 @@ class ReactivePlannerB200:
         """reactive_planner.py:184-272: statistics, all_traj, selection (device arg-min == first collision-free
         entry of the cost-sorted feasible list)."""
         self._collision_counter = res.collision_counter
+        if res.argmin is not None and int(res.argmin) >= 0:
+            bundle.winner_row = int(res.argmin) - bundle.row_base
         counts = [0] * 11
         if self._multiproc and self._kinematic_debug:          # only then do the per-reason counts travel back
             counts = [int(v) for v in res.reason_counts]       # (reactive_planner.py:218-220)

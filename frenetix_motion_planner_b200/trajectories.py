@@ -231,6 +231,7 @@ class TrajectoryBundle:
         self._members: Optional[np.ndarray] = None
         self._cache: Dict[int, TrajectorySample] = {}
         self._is_sorted = False
+        self.winner_row: Optional[int] = None     # local row of the last plan's arg-min (set by the planner)
 
     # ---- bulk, lazily read back ------------------------------------------------------------
     def _read_flags(self):
@@ -262,6 +263,9 @@ class TrajectoryBundle:
         return self._total
 
     def states_of(self, row: int) -> np.ndarray:
+        if self.winner_row is not None and int(row) == self.winner_row:
+            # the selected candidate's rows came back with the arg-min (mapped result record): no device round trip
+            return self._h.winner_states()
         return self._h.get_states(np.array([row], dtype=np.int64))[:, 0, :]
 
     def states(self, rows, fields=None) -> np.ndarray:
