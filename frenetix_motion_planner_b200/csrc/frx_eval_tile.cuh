@@ -213,148 +213,6 @@ struct FrxLaneOut {
     bool t_missing;
 };
 
-// ------------------------------------------------------------------------------------------------------------
-// second pass over a candidate's time steps [i0, i1): prediction cost, distance to obstacles, collision sweep.
-// A function of its own (not inlined) so that its registers are allocated independently of the step loop's.
-// ------------------------------------------------------------------------------------------------------------
-template <int SEG, bool OBS, bool XCOST>
-__device__ __noinline__ void frx_obstacle_pass(const FrxKernelArgs& A, const double* __restrict__ sp, const size_t fstride,
-                                               const long long Np, const int i0, const int i1, const int Nt, const bool need_pred,
-                                               const bool need_d2o, const bool need_col, double& pred_sum_o, double& d2o_sum_o,
-                                               bool& collide_o, bool& boundary_o) {
-    double pred_sum = 0.0, d2o_sum = 0.0;
-    bool collide = false, boundary = false;
-    {
-            double pbx = 0, pby = 0, pux = 0, puy = 0;   // ego box of the previous step
-            if (SEG > 1 && need_col && i0 >= 1 && i0 < i1) {      // ... which another lane wrote for a later segment
-                const double* qp = sp + (size_t)(i0 - 1) * (size_t)Np;
-                double sn, cs;
-                sincos(__ldcg(qp + 2 * fstride), &sn, &cs);
-                pbx = __ldcg(qp) + A.wb_rear * cs; pby = __ldcg(qp + fstride) + A.wb_rear * sn; pux = cs; puy = sn;
-            }
-            // x, y, theta of the candidate come back from the state tensor (L2), loaded ONE STEP AHEAD of their use
-            const double* q = sp + (size_t)i0 * (size_t)Np;
-            double x_n = 0.0, y_n = 0.0, th_n = 0.0;
-            if (i0 < i1) { x_n = __ldcg(q); y_n = __ldcg(q + fstride); if (need_col) th_n = __ldcg(q + 2 * fstride); }
-            for (int i = i0; i < i1; ++i, q += Np) {
-                const double x = x_n, y = y_n, th = th_n;
-                if (i + 1 < i1) {
-                    x_n = __ldcg(q + Np); y_n = __ldcg(q + Np + fstride);
-                    if (need_col) th_n = __ldcg(q + Np + 2 * fstride);
-                }
-#if FRX_OPT_OBS_PREFETCH
-                // the records of the NEXT step go to L1 now (warp-uniform addresses: one request per 128-byte line), so
-                // the loops of the next iteration hit L1 instead of waiting for L2 on every group of loads
-                if (OBS && i + 1 < i1) {
-                    if (need_pred) {
-                        const char* pf = reinterpret_cast<const char*>(A.opred + (size_t)i * A.O * 8);
-                        const int nb = __ldg(A.on_pred + i) * 64;
-                        for (int b = 0; b < nb; b += 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(pf + b));
-                    }
-                    if (need_col && i >= 1) {
-                        const char* pf = reinterpret_cast<const char*>(A.ohull + (size_t)(i - 1) * A.O * 8);
-                        const int nb = __ldg(A.on_hull + (i - 1)) * 64;
-                        for (int b = 0; b < nb; b += 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(pf + b));
-                    }
-                }
-#endif
-                if (need_pred && i >= 1) {
-                    // the obstacles predicted at this step: 64-byte records, warp-uniform 16-byte loads
-                    const int n = __ldg(A.on_pred + (i - 1));
-                    const double2* __restrict__ rec = reinterpret_cast<const double2*>(A.opred + (size_t)(i - 1) * A.O * 8);
-                    // branch-free body (loads of the unrolled records issue together, the reciprocal chains overlap);
-                    // an operand outside the fast reciprocal's range (0, inf, nan, denormal: the ego ON an obstacle
-                    // mean) is only recorded -- the step is then redone with IEEE division
-                    const double saved = pred_sum;
-                    bool ok = true;
-#pragma unroll 4
-                    for (int o = 0; o < n; ++o) {
-                        const double2 pp = __ldg(rec + 4 * o), va = __ldg(rec + 4 * o + 1), vb = __ldg(rec + 4 * o + 2);   // (px,py) (iv00,iv10) (iv01,iv11)
-                        double ex = x - pp.x;
-                        double ey = y - pp.y;
-                        double t0 = ex * va.x + ey * va.y;
-                        double t1 = ex * vb.x + ey * vb.y;
-                        double m = t0 * ex + t1 * ey;
-                        double m2 = m * m;
-                        ok = ok && drcp_in_range(m2);
-                        pred_sum += drcp_unchecked(m2);
-                    }
-                    if (!ok) {
-                        pred_sum = saved;
-                        for (int o = 0; o < n; ++o) {
-                            const double2 pp = __ldg(rec + 4 * o), va = __ldg(rec + 4 * o + 1), vb = __ldg(rec + 4 * o + 2);
-                            double ex = x - pp.x;
-                            double ey = y - pp.y;
-                            double t0 = ex * va.x + ey * va.y;
-                            double t1 = ex * vb.x + ey * vb.y;
-                            double m = t0 * ex + t1 * ey;
-                            pred_sum += drcpg(m * m);
-                        }
-                    }
-                }
-                if (need_d2o) {
-                    for (int o = 0; o < A.n_obs_pos; ++o) {
-                        double ex = x - __ldg(A.obs_pos + 2 * o), ey = y - __ldg(A.obs_pos + 2 * o + 1);
-                        double dist = sqrt(ex * ex + ey * ey);
-                        d2o_sum += ddivg(1.0, dist * dist);
-                    }
-                }
-                if (need_col) {
-                    double sn, cs;
-                    sincos(th, &sn, &cs);
-                    const double bx = x + A.wb_rear * cs, by = y + A.wb_rear * sn;     // state.py:30-39 rear axle -> centre
-                    if (i >= 1 && !(collide && (boundary || A.B == 0))) {
-                        const int k = i - 1;                                            // hull of boxes k, k + 1
-                        Hull e = obb_sum_hull(pbx, pby, pux, puy, bx, by, cs, sn, A.half_len, A.half_wid);
-                        const double er = sqrt(e.ha * e.ha + e.hb * e.hb) * (1.0 + 1e-9);
-                        if (k >= 1 && !collide) {
-                            // obstacle hulls of step k - 1 (hull record: cx, cy, r | ux, uy | ha, hb)
-                            const int n = __ldg(A.on_hull + (k - 1));
-                            const double2* __restrict__ rec = reinterpret_cast<const double2*>(A.ohull + (size_t)(k - 1) * A.O * 8);
-                            // conservative broad phase over all hulls of the step, branch-free (bounding circles, 32
-                            // hulls per mask word); the exact separating-axis test runs for the few that pass
-                            for (int o0 = 0; o0 < n && !collide; o0 += 32) {
-                                const int nn = (n - o0 < 32) ? (n - o0) : 32;
-                                unsigned near_mask = 0;
-#pragma unroll 4
-                                for (int o = 0; o < nn; ++o) {
-                                    const double2 cc = __ldg(rec + 4 * (o0 + o));
-                                    const double hr = __ldg(reinterpret_cast<const double*>(rec + 4 * (o0 + o) + 1));
-                                    double rr = er + hr;
-                                    double ddx = cc.x - e.cx, ddy = cc.y - e.cy;
-                                    near_mask |= (ddx * ddx + ddy * ddy > rr * rr) ? 0u : (1u << o);
-                                }
-                                while (near_mask) {
-                                    const int o = o0 + __ffs(near_mask) - 1;
-                                    near_mask &= near_mask - 1;
-                                    const double2 cc = __ldg(rec + 4 * o), ru = __ldg(rec + 4 * o + 1), uh = __ldg(rec + 4 * o + 2);
-                                    if (obb_overlap(e, cc.x, cc.y, ru.y, uh.x, uh.y, __ldg(reinterpret_cast<const double*>(rec + 4 * o + 3)))) {
-                                        collide = true;
-                                        break;
-                                    }
-                                }
-                            }
-                        }
-                        if (!boundary) {
-                            for (int b = 0; b < A.B; ++b) {
-                                const double* __restrict__ sb = A.sobb + b * 8;
-                                double rr = er + __ldg(sb + 6);
-                                double ddx = __ldg(sb) - e.cx, ddy = __ldg(sb + 1) - e.cy;
-                                if (ddx * ddx + ddy * ddy > rr * rr) continue;
-                                if (obb_overlap(e, __ldg(sb), __ldg(sb + 1), __ldg(sb + 2), __ldg(sb + 3), __ldg(sb + 4), __ldg(sb + 5))) {
-                                    boundary = true;
-                                    break;
-                                }
-                            }
-                        }
-                    }
-                    pbx = bx; pby = by; pux = cs; puy = sn;
-                }
-            }
-    }
-    pred_sum_o = pred_sum; d2o_sum_o = d2o_sum; collide_o = collide; boundary_o = boundary;
-}
-
 // `pass` = the lanes executing this call together (all SEG lanes of a candidate are among them): the mask of every
 // shuffle below, which all of them reach -- there is no early return.
 template <int SEG, bool OBS, bool XCOST>
@@ -749,9 +607,133 @@ __device__ __forceinline__ FrxLaneOut frx_candidate(const FrxKernelArgs& A, cons
         const bool need_pred = OBS && costed && (cost_mask & (1u << FRX_COST_PREDICTION)) && A.O > 0;
         const bool need_d2o = XCOST && costed && (cost_mask & (1u << FRX_COST_DISTANCE_TO_OBSTACLES)) && A.n_obs_pos > 0;
         const bool need_col = OBS && candidate && A.check_collisions && (A.O > 0 || A.B > 0);
-        if (need_pred || need_d2o || need_col)
-            frx_obstacle_pass<SEG, OBS, XCOST>(A, sp, fstride, Np, i0, i1, Nt, need_pred, need_d2o, need_col, pred_sum, d2o_sum, collide,
-                                               boundary);
+        if (need_pred || need_d2o || need_col) {
+            double pbx = 0, pby = 0, pux = 0, puy = 0;   // ego box of the previous step
+            if (SEG > 1 && need_col && i0 >= 1 && i0 < i1) {      // ... which another lane wrote for a later segment
+                const double* qp = sp + (size_t)(i0 - 1) * (size_t)Np;
+                double sn, cs;
+                sincos(__ldcg(qp + 2 * fstride), &sn, &cs);
+                pbx = __ldcg(qp) + A.wb_rear * cs; pby = __ldcg(qp + fstride) + A.wb_rear * sn; pux = cs; puy = sn;
+            }
+            // x, y, theta of the candidate come back from the state tensor (L2), loaded ONE STEP AHEAD of their use
+            const double* q = sp + (size_t)i0 * (size_t)Np;
+            double x_n = 0.0, y_n = 0.0, th_n = 0.0;
+            if (i0 < i1) { x_n = __ldcg(q); y_n = __ldcg(q + fstride); if (need_col) th_n = __ldcg(q + 2 * fstride); }
+            for (int i = i0; i < i1; ++i, q += Np) {
+                const double x = x_n, y = y_n, th = th_n;
+                if (i + 1 < i1) {
+                    x_n = __ldcg(q + Np); y_n = __ldcg(q + Np + fstride);
+                    if (need_col) th_n = __ldcg(q + Np + 2 * fstride);
+                }
+#if FRX_OPT_OBS_PREFETCH
+                // the records of the NEXT step go to L1 now (warp-uniform addresses: one request per 128-byte line), so
+                // the loops of the next iteration hit L1 instead of waiting for L2 on every group of loads
+                if (OBS && i + 1 < i1) {
+                    if (need_pred) {
+                        const char* pf = reinterpret_cast<const char*>(A.opred + (size_t)i * A.O * 8);
+                        const int nb = __ldg(A.on_pred + i) * 64;
+                        for (int b = 0; b < nb; b += 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(pf + b));
+                    }
+                    if (need_col && i >= 1) {
+                        const char* pf = reinterpret_cast<const char*>(A.ohull + (size_t)(i - 1) * A.O * 8);
+                        const int nb = __ldg(A.on_hull + (i - 1)) * 64;
+                        for (int b = 0; b < nb; b += 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(pf + b));
+                    }
+                }
+#endif
+                if (need_pred && i >= 1) {
+                    // the obstacles predicted at this step: 64-byte records, warp-uniform 16-byte loads
+                    const int n = __ldg(A.on_pred + (i - 1));
+                    const double2* __restrict__ rec = reinterpret_cast<const double2*>(A.opred + (size_t)(i - 1) * A.O * 8);
+                    // branch-free body (loads of the unrolled records issue together, the reciprocal chains overlap);
+                    // an operand outside the fast reciprocal's range (0, inf, nan, denormal: the ego ON an obstacle
+                    // mean) is only recorded -- the step is then redone with IEEE division
+                    const double saved = pred_sum;
+                    bool ok = true;
+#pragma unroll 4
+                    for (int o = 0; o < n; ++o) {
+                        const double2 pp = __ldg(rec + 4 * o), va = __ldg(rec + 4 * o + 1), vb = __ldg(rec + 4 * o + 2);   // (px,py) (iv00,iv10) (iv01,iv11)
+                        double ex = x - pp.x;
+                        double ey = y - pp.y;
+                        double t0 = ex * va.x + ey * va.y;
+                        double t1 = ex * vb.x + ey * vb.y;
+                        double m = t0 * ex + t1 * ey;
+                        double m2 = m * m;
+                        ok = ok && drcp_in_range(m2);
+                        pred_sum += drcp_unchecked(m2);
+                    }
+                    if (!ok) {
+                        pred_sum = saved;
+                        for (int o = 0; o < n; ++o) {
+                            const double2 pp = __ldg(rec + 4 * o), va = __ldg(rec + 4 * o + 1), vb = __ldg(rec + 4 * o + 2);
+                            double ex = x - pp.x;
+                            double ey = y - pp.y;
+                            double t0 = ex * va.x + ey * va.y;
+                            double t1 = ex * vb.x + ey * vb.y;
+                            double m = t0 * ex + t1 * ey;
+                            pred_sum += drcpg(m * m);
+                        }
+                    }
+                }
+                if (need_d2o) {
+                    for (int o = 0; o < A.n_obs_pos; ++o) {
+                        double ex = x - __ldg(A.obs_pos + 2 * o), ey = y - __ldg(A.obs_pos + 2 * o + 1);
+                        double dist = sqrt(ex * ex + ey * ey);
+                        d2o_sum += ddivg(1.0, dist * dist);
+                    }
+                }
+                if (need_col) {
+                    double sn, cs;
+                    sincos(th, &sn, &cs);
+                    const double bx = x + A.wb_rear * cs, by = y + A.wb_rear * sn;     // state.py:30-39 rear axle -> centre
+                    if (i >= 1 && !(collide && (boundary || A.B == 0))) {
+                        const int k = i - 1;                                            // hull of boxes k, k + 1
+                        Hull e = obb_sum_hull(pbx, pby, pux, puy, bx, by, cs, sn, A.half_len, A.half_wid);
+                        const double er = sqrt(e.ha * e.ha + e.hb * e.hb) * (1.0 + 1e-9);
+                        if (k >= 1 && !collide) {
+                            // obstacle hulls of step k - 1 (hull record: cx, cy, r | ux, uy | ha, hb)
+                            const int n = __ldg(A.on_hull + (k - 1));
+                            const double2* __restrict__ rec = reinterpret_cast<const double2*>(A.ohull + (size_t)(k - 1) * A.O * 8);
+                            // conservative broad phase over all hulls of the step, branch-free (bounding circles, 32
+                            // hulls per mask word); the exact separating-axis test runs for the few that pass
+                            for (int o0 = 0; o0 < n && !collide; o0 += 32) {
+                                const int nn = (n - o0 < 32) ? (n - o0) : 32;
+                                unsigned near_mask = 0;
+#pragma unroll 4
+                                for (int o = 0; o < nn; ++o) {
+                                    const double2 cc = __ldg(rec + 4 * (o0 + o));
+                                    const double hr = __ldg(reinterpret_cast<const double*>(rec + 4 * (o0 + o) + 1));
+                                    double rr = er + hr;
+                                    double ddx = cc.x - e.cx, ddy = cc.y - e.cy;
+                                    near_mask |= (ddx * ddx + ddy * ddy > rr * rr) ? 0u : (1u << o);
+                                }
+                                while (near_mask) {
+                                    const int o = o0 + __ffs(near_mask) - 1;
+                                    near_mask &= near_mask - 1;
+                                    const double2 cc = __ldg(rec + 4 * o), ru = __ldg(rec + 4 * o + 1), uh = __ldg(rec + 4 * o + 2);
+                                    if (obb_overlap(e, cc.x, cc.y, ru.y, uh.x, uh.y, __ldg(reinterpret_cast<const double*>(rec + 4 * o + 3)))) {
+                                        collide = true;
+                                        break;
+                                    }
+                                }
+                            }
+                        }
+                        if (!boundary) {
+                            for (int b = 0; b < A.B; ++b) {
+                                const double* __restrict__ sb = A.sobb + b * 8;
+                                double rr = er + __ldg(sb + 6);
+                                double ddx = __ldg(sb) - e.cx, ddy = __ldg(sb + 1) - e.cy;
+                                if (ddx * ddx + ddy * ddy > rr * rr) continue;
+                                if (obb_overlap(e, __ldg(sb), __ldg(sb + 1), __ldg(sb + 2), __ldg(sb + 3), __ldg(sb + 4), __ldg(sb + 5))) {
+                                    boundary = true;
+                                    break;
+                                }
+                            }
+                        }
+                    }
+                    pbx = bx; pby = by; pux = cs; puy = sn;
+                }
+            }
         }
     }
 
