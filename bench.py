@@ -477,6 +477,20 @@ def main():
         stream.synchronize()
         torch.cuda.synchronize()
         e2e_s = time.perf_counter() - t0
+        # ---- for information (N = 1, cartesian workloads): the same plan through frx_plan_grid, i.e. handing the
+        # library the three host axes + x_cl the planner owns instead of the expanded [N, 13] matrix
+        e2e_grid_s, grid_same = None, None
+        if world == 1 and not grid_mode and first == 0 and count == len(w["t1"]) * len(w["v1"]) * len(w["d1"]):
+            def step_grid():
+                rg = h.plan_grid(w["t1"], w["v1"], w["d1"], w["x_cl"])
+                return rg, (h.winner_states() if rg.argmin >= 0 else None)
+            for _ in range(3):
+                rg, _w = step_grid()
+            t0 = time.perf_counter()
+            for i in range(args.steps):
+                rg, _w = step_grid()
+            e2e_grid_s = time.perf_counter() - t0
+            grid_same = bool(rg.argmin == r_e2e.argmin and rg.min_cost == r_e2e.min_cost)
         if world > 1:
             dist.barrier()
         clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
@@ -527,6 +541,11 @@ def main():
                     "d2h_bytes_per_step": int(16 + 8 * 17 + 14 * 32 * 8),
                     "ms_per_step": 1e3 * e2e_s / args.steps, "eval_kernel_ms": float(np.mean(e2e_kern_ms)),
                     "device_ms": float(np.mean(e2e_dev_ms)),
+                    "grid_api": (None if e2e_grid_s is None else
+                                 {"value": count * args.steps / e2e_grid_s, "unit": UNIT, "h2d_bytes_per_step":
+                                  int(8 * (len(w["t1"]) + len(w["v1"]) + len(w["d1"]) + 6)),
+                                  "note": "same plan through frx_plan_grid (host axes t1/ss1/d1 + x_cl, rows expanded on "
+                                          "the device)", "same_argmin_and_cost_as_matrix_api": grid_same}),
                     "note": ("frx_plan_grid on HOST axes t1/ss1/d1 + x_cl (rows expanded on the device); " if grid_mode else
                              "frx_plan on a PINNED HOST sampling matrix: the eval kernel reads the rows in place over PCIe "
                              "(cp.async prefetch one tile ahead, no staging copy; FRX_ZEROCOPY=0 restores cudaMemcpyAsync); ") +

@@ -109,3 +109,16 @@ def test_pinned_host_matrix_is_read_in_place():
     res2 = h.plan(Sp.numpy()[3:])
     d2 = device_plan(S[3:], ref, prm, preds)
     assert int(res2.argmin) == d2["argmin"] and float(res2.min_cost) == d2["min_cost"]
+
+
+@pytest.mark.parametrize("seg", [1, 2, 4])
+@pytest.mark.parametrize("name", ["arc_hv_draw_pred", "scurve_lowvel_draw", "scurve_brake_hv_nodraw_nodebug", "tjunction_draw"])
+def test_every_lanes_per_candidate_instance_matches_oracle(name, seg, monkeypatch):
+    """SEG = 1, 2, 4 lanes per candidate (time steps split into segments) are separate kernel instances; the library picks
+    one from the row count, FRX_SEG forces it.  All three must satisfy the parity contract, ragged last tile included."""
+    monkeypatch.setenv("FRX_SEG", str(seg))
+    g, ref, prm, preds = load_golden(name)
+    S = np.ascontiguousarray(np.tile(g["sampling"], (3, 1))[:g["sampling"].shape[0] * 2 + 7])
+    ora = fo.plan(S, ref, prm, preds)
+    dev = device_plan(S, ref, prm, preds)
+    compare_with_oracle(dev, ora, prm)       # asserts the contract (exact masks / index, 1e-6 on states and costs)
