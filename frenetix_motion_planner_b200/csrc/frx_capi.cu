@@ -30,6 +30,8 @@ void frx_launch_gather(const double* states, long long Np, int Nt, int Ntp, cons
                        long long n_idx, uint32_t mask, double* out, cudaStream_t st);
 void frx_features(const FrxKernelArgs& a, bool* obs, bool* xcost);
 int frx_pick_seg(long long n_rows, int sm_count);
+cudaError_t frx_launch_obstacle_pass(const FrxKernelArgs& a, int sm_count, cudaStream_t st);
+int frx_obstacle_pass_max_grid(int sm_count);
 
 void frx_launch_selftest_fdiv(long long n, const double* a, const double* b, double* q1, double* q2, cudaStream_t st);
 void frx_launch_selftest_divc(long long n, const double* a, double b, double* q1, double* q2, cudaStream_t st);
@@ -424,8 +426,23 @@ static int enqueue_plan(frx_ctx* ctx, long long N, const double* d_sampling, boo
     CK(cudaMemsetAsync(trace.p, 0, n_tr * 8, st));
     a.trace = trace.p;
 #endif
+    // Large plans with obstacle work: the obstacle pass, the arg-min and the result record run as a second kernel
+    // (frx_obstacle_kernel, see there for why).  FRX_SPLIT_OBS=0/1 forces the choice.
+    {
+        bool obs, xc;
+        frx_features(a, &obs, &xc);
+        bool d2o = false;
+        for (int k = 0; k < a.n_costs; ++k) d2o |= (a.cost_ids[k] == FRX_COST_DISTANCE_TO_OBSTACLES) && a.n_obs_pos > 0;
+        bool split = (obs || d2o) && a.seg == 1;
+        if (const char* e = getenv("FRX_SPLIT_OBS")) split = (obs || d2o) && e[0] == '1';
+        a.defer_obs = split ? 1 : 0;
+    }
+    if (a.defer_obs) CK(ctx->blockbest.reserve((size_t)frx_obstacle_pass_max_grid(ctx->sm_count) > (size_t)grid
+                                                   ? (size_t)frx_obstacle_pass_max_grid(ctx->sm_count) : (size_t)grid));
+    a.blockbest = ctx->blockbest.p;
     CK(cudaEventRecord(ctx->evk0, st));
     CK(frx_launch_eval(a, nchunk, grid, st));
+    if (a.defer_obs) CK(frx_launch_obstacle_pass(a, ctx->sm_count, st));
     CK(cudaEventRecord(ctx->evk1, st));
 #ifdef FRX_TRACE
     {

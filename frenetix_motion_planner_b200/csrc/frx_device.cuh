@@ -14,6 +14,9 @@
 #define FRX_MIN_CTAS2 ((FRX_MIN_CTAS > 3) ? (FRX_MIN_CTAS - 2) : 1)
 #endif
 #define FRX_MAX_T_VALUES 128
+#ifndef FRX_OBS_MIN_CTAS
+#define FRX_OBS_MIN_CTAS 3   // resident 256-thread blocks per SM the obstacle kernel is compiled for (register cap 85)
+#endif
 #ifndef FRX_CHUNK_ROWS
 #define FRX_CHUNK_ROWS 8
 #endif
@@ -94,6 +97,8 @@ struct FrxKernelArgs {
     double* states;         // [14][Nt][Np]: field, step, candidate (candidate fastest, Np = N rounded up to 32)
     long long Np;
     int seg;                // lanes per candidate (1, 2 or 4): which kernel instance runs, tile = 32 / seg rows
+    int defer_obs;          // 1: the eval kernel skips the obstacle pass, arg-min and result record; frx_obstacle_kernel
+                            //    (launched right behind it) does them
     int keep_xyt;           // store_states == 0 but the obstacle pass needs the x, y, theta planes
     double* costs;          // [N][n_costs]
     double* total;          // [N]

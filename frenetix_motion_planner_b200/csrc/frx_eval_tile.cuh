@@ -607,7 +607,7 @@ __device__ __forceinline__ FrxLaneOut frx_candidate(const FrxKernelArgs& A, cons
         const bool need_pred = OBS && costed && (cost_mask & (1u << FRX_COST_PREDICTION)) && A.O > 0;
         const bool need_d2o = XCOST && costed && (cost_mask & (1u << FRX_COST_DISTANCE_TO_OBSTACLES)) && A.n_obs_pos > 0;
         const bool need_col = OBS && candidate && A.check_collisions && (A.O > 0 || A.B > 0);
-        if (need_pred || need_d2o || need_col) {
+        if ((need_pred || need_d2o || need_col) && !A.defer_obs) {      // deferred: frx_obstacle_kernel does this pass
             double pbx = 0, pby = 0, pux = 0, puy = 0;   // ego box of the previous step
             if (SEG > 1 && need_col && i0 >= 1 && i0 < i1) {      // ... which another lane wrote for a later segment
                 const double* qp = sp + (size_t)(i0 - 1) * (size_t)Np;
@@ -809,7 +809,7 @@ __device__ __forceinline__ FrxLaneOut frx_candidate(const FrxKernelArgs& A, cons
     ev |= ((fl >> 2) & 0x3ffu) << CNT_REASON1;      // reason bits 1..10 -> slots CNT_REASON1..+9
     out.ev = ev;
     out.total = total;
-    out.winner_ok = candidate && !collide && !boundary;
+    out.winner_ok = candidate && !collide && !boundary && !A.defer_obs;    // deferred: the obstacle kernel selects
     return out;
 }
 
@@ -1026,6 +1026,7 @@ __device__ __forceinline__ void frx_tile_body(const FrxKernelArgs& A, const int 
     if (threadIdx.x < CNT_REASON1 + 10)
         A.blockcnt[(size_t)cta_local * (CNT_REASON1 + 10) + threadIdx.x] = s_cnt[threadIdx.x];
     __syncthreads();
+    if (A.defer_obs) return;     // the obstacle kernel finishes the plan (arg-min, counters, result record)
     __shared__ int s_is_last;
     if (threadIdx.x == 0) {
         FrxBest b = s_best[0];

@@ -122,3 +122,23 @@ def test_every_lanes_per_candidate_instance_matches_oracle(name, seg, monkeypatc
     ora = fo.plan(S, ref, prm, preds)
     dev = device_plan(S, ref, prm, preds)
     compare_with_oracle(dev, ora, prm)       # asserts the contract (exact masks / index, 1e-6 on states and costs)
+
+
+@pytest.mark.parametrize("name", ["arc_hv_draw_pred", "arc_hv_nodraw_nodebug", "tjunction_draw", "tjunction_nodraw"])
+def test_split_obstacle_kernel_equals_fused_pass(name, monkeypatch):
+    """Large plans run the obstacle pass + arg-min as a second kernel (FRX_SPLIT_OBS forces it here): every output is
+    bit-identical to the fused pass, and the oracle contract holds."""
+    g, ref, prm, preds = load_golden(name)
+    S = np.ascontiguousarray(np.tile(g["sampling"], (4, 1))[:g["sampling"].shape[0] * 3 + 11])
+    monkeypatch.setenv("FRX_SEG", "1")
+    monkeypatch.setenv("FRX_SPLIT_OBS", "0")
+    fused = device_plan(S, ref, prm, preds)
+    monkeypatch.setenv("FRX_SPLIT_OBS", "1")
+    split = device_plan(S, ref, prm, preds)
+    for k in ("flags", "traj_len", "costs", "total", "states", "reason_counts"):
+        assert np.array_equal(fused[k], split[k]), k
+    for k in ("argmin", "min_cost", "n_in_list", "n_feasible", "collision_counter"):
+        assert fused[k] == split[k], k
+    assert fused["res"].n_collide == split["res"].n_collide and fused["res"].n_boundary == split["res"].n_boundary
+    assert np.array_equal(fused["handler"].winner_states(), split["handler"].winner_states())
+    compare_with_oracle(split, fo.plan(S, ref, prm, preds), prm)
