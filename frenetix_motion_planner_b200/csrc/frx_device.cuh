@@ -10,18 +10,9 @@
 #ifndef FRX_MIN_CTAS
 #define FRX_MIN_CTAS 2   // resident CTAs per SM the eval kernel is compiled for (register cap 168)
 #endif
-#ifndef FRX_MIN_CTAS2    // ... and the 64-step instance (two chunks per candidate, more live registers)
-#define FRX_MIN_CTAS2 ((FRX_MIN_CTAS > 3) ? (FRX_MIN_CTAS - 2) : 1)
-#endif
 #define FRX_MAX_T_VALUES 128
 #ifndef FRX_OBS_MIN_CTAS
 #define FRX_OBS_MIN_CTAS 3   // resident 256-thread blocks per SM the obstacle kernel is compiled for (register cap 85)
-#endif
-#ifndef FRX_CHUNK_ROWS
-#define FRX_CHUNK_ROWS 8
-#endif
-#ifndef FRX_GUIDED
-#define FRX_GUIDED 1     // 1: chunk sizes shrink towards the end of the row range (guided self-scheduling)
 #endif
 #define FRX_EPS 1e-5
 

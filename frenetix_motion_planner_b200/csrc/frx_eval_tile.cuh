@@ -40,15 +40,6 @@ __device__ __forceinline__ unsigned long long frx_now() {
 #else
 #define FRX_STAMP(k) do { } while (0)
 #endif
-#ifndef FRX_OPT_FASTSTEP
-#define FRX_OPT_FASTSTEP 1
-#endif
-#ifndef FRX_STEP_UNROLL
-#define FRX_STEP_UNROLL 1
-#endif
-#ifndef FRX_OPT_OBS_PREFETCH
-#define FRX_OPT_OBS_PREFETCH 0     // measured: prefetching the next step's obstacle records into L1 changes nothing
-#endif
 
 enum { M_S = 0, M_SD, M_SDD, M_INTERP, M_KR, M_KRD, M_PX, M_PY, M_SN, M_CS, M_T1, M_T2, M_T3, M_T4, M_T5, M_FIELDS };
 
@@ -298,7 +289,7 @@ __device__ __forceinline__ FrxLaneOut frx_candidate(const FrxKernelArgs& A, cons
             if (sdj > 0.001) {
                 double ddj = 0.0;
                 if (j < traj_len) ddj = poly_vel(Q, mt[M_T1 * TP + j], mt[M_T2 * TP + j], mt[M_T3 * TP + j], mt[M_T4 * TP + j]);
-                th_prev = atan(ddivf(ddj, sdj)) + mt[M_INTERP * TP + j];
+                th_prev = datan(ddivf(ddj, sdj)) + mt[M_INTERP * TP + j];
                 break;
             }
         }
@@ -319,10 +310,7 @@ __device__ __forceinline__ FrxLaneOut frx_candidate(const FrxKernelArgs& A, cons
     const int nA = Nt, nbA = (nA & 1) ? nA : (nA - 1);            // integrands sampled at every step
     const int nD = Nt - 1, nbD = (nD & 1) ? nD : (nD - 1);        // integrands built from np.diff
 
-    constexpr int kStepUnroll = FRX_STEP_UNROLL;
-#pragma unroll kStepUnroll
     for (int i = i0; i < i1; ++i) {
-#if FRX_OPT_FASTSTEP
         // ---- the common case as ONE straight-line block (selects, no branches), so that the independent fp64 chains
         // (the two slope divisions, atan, the reciprocal square root, the 1/qc refinement, the a_max(v) quotient) overlap
         // instead of running one after the other behind reconvergence points; the rare cases -- stand-still step in
@@ -353,7 +341,7 @@ __device__ __forceinline__ FrxLaneOut frx_candidate(const FrxKernelArgs& A, cons
             dp = low ? ddi : dph;
             dpp = low ? dddi : (mov ? qb : 0.);
         }
-        double th_cl = atan(dp);                     // np.arctan2(dp, 1.0)
+        double th_cl = datan(dp);                     // np.arctan2(dp, 1.0)
         double th_gl = th_cl + interp;
         const double oneKrD = 1 - k_r * di;
         const double w = 1.0 + dp * dp;
@@ -414,94 +402,6 @@ __device__ __forceinline__ FrxLaneOut frx_candidate(const FrxKernelArgs& A, cons
         } else {
             xi = 0.0; yi = 0.0; th_gl = 0.0; th_cl = 0.0; vi = 0.0; ai = 0.0; kappa = 0.0; kd = 0.0;
         }
-#else
-        const double si = mt[M_S * TP + i], sdi = mt[M_SD * TP + i], sddi = mt[M_SDD * TP + i];
-        double di = 0, ddi = 0, dddi = 0;
-        if (i < traj_len) {
-            if (!low) {
-                double t = mt[M_T1 * TP + i], t2 = mt[M_T2 * TP + i], t3 = mt[M_T3 * TP + i], t4 = mt[M_T4 * TP + i],
-                       t5 = mt[M_T5 * TP + i];
-                di = poly_pos(Q, t, t2, t3, t4, t5);
-                ddi = poly_vel(Q, t, t2, t3, t4);
-                dddi = poly_acc(Q, t, t2, t3);
-            } else {
-                double q1 = si - s_first, q2 = q1 * q1, q3 = q2 * q1, q4 = q2 * q2, q5 = q4 * q1;
-                di = poly_pos(Q, q1, q2, q3, q4, q5);
-                ddi = poly_vel(Q, q1, q2, q3, q4);
-                dddi = poly_acc(Q, q1, q2, q3);
-            }
-        } else {
-            di = d_last;
-        }
-        double xi = 0.0, yi = 0.0, th_gl = 0.0, th_cl = 0.0, vi = 0.0, ai = 0.0, kappa = 0.0, kd = 0.0;
-        if (evaluate) {
-            double dp, dpp;
-            const bool mov = sdi > 0.001;
-            if (!low) {
-                dp = mov ? ddivf(ddi, sdi) : 0.;
-                double ddot = dddi - dp * sddi;
-                dpp = mov ? ddivf(ddot, sdi * sdi) : 0.;
-            } else {
-                dp = ddi; dpp = dddi;
-            }
-            const double interp = mt[M_INTERP * TP + i];
-            // :423-454 orientations; stand-still in high-velocity mode keeps the previous global orientation
-            const bool direct = mov || low;
-            if (direct) { th_cl = atan(dp); th_gl = th_cl + interp; }   // np.arctan2(dp, 1.0)
-            else { th_gl = th_prev; th_cl = th_gl - interp; }
-            // :457-478
-            const double k_r = mt[M_KR * TP + i], k_r_d = mt[M_KRD * TP + i];
-            double oneKrD = 1 - k_r * di;
-            // cos, tan and 1/cos of theta_cl.  On the direct branch theta_cl = atan(dp), so with w = 1 + dp^2:
-            // cos = 1/sqrt(w), 1/cos = sqrt(w), tan = dp hold algebraically (same <= 1-2 ulp error class as
-            // libm's cos/tan of the rounded angle); only the stand-still branch needs real trigonometry.
-            double cosT, tanT, secT;
-            if (direct) {
-                double w = 1.0 + dp * dp;
-                cosT = rsqrt(w);
-                secT = w * cosT;
-                tanT = dp;
-            } else {
-                double sT;
-                sincos(th_cl, &sT, &cosT);
-                secT = ddivg(1.0, cosT);
-                tanT = sT * secT;
-            }
-            double qc = oneKrD * secT;            // oneKrD / cos(theta_cl)
-            double cq = ddivg(1.0, qc);           // cos(theta_cl) / oneKrD
-            kappa = (dpp + (k_r * dp + k_r_d * di) * tanT) * cosT * (cq * cq) + cq * k_r;
-            vi = sdi * qc;
-            ai = sddi * qc + ((sdi * sdi) * secT) * (oneKrD * tanT * (kappa * qc - k_r) - (k_r_d * di + k_r * dp));
-            // :483-533 gates
-            uint32_t g = 0;
-            if (vi < -FRX_EPS) g |= 1u;
-            if (fabs(kappa) > A.kappa_max) g |= 2u;
-            const bool deferred = (SEG > 1) && (i == i0) && (seg > 0);
-            const bool has_prev = (i > 0) && !deferred;
-            double yaw_rate = has_prev ? ddivc(th_gl - th_prev, dT, A.inv_dt) : 0.;
-            double theta_dot_max = A.kappa_max * vi;
-            if (fabs(ddivc(rint(yaw_rate * 100000.0), 100000.0, 1e-5)) > theta_dot_max) g |= 4u;
-            double kappa_dot = has_prev ? ddivc(kappa - ka_prev, dT, A.inv_dt) : 0.;
-            if (fabs(kappa_dot) > 0.4) g |= 8u;
-            double a_hi = (vi > A.v_switch) ? ddivg(A.a_max * A.v_switch, vi) : A.a_max;
-            if (!(-A.a_max <= ai && ai <= a_hi)) g |= 16u;
-            if (deferred) {
-                g_first = g; th_first = th_gl; ka_first = kappa; vi_first = vi; a_first = ai; thc_first = th_cl;
-            } else if (brk) {
-                if (!gate_hit && g) { gate_or = g & (~g + 1u); gate_hit = true; }   // first violating step, its first gate only
-            } else {
-                gate_or |= g;
-            }
-            // :536-547 Cartesian position: zero from the first out-of-domain step on
-            if (i < first_none) {
-                xi = mt[M_PX * TP + i] - di * mt[M_SN * TP + i];
-                yi = mt[M_PY * TP + i] + di * mt[M_CS * TP + i];
-            }
-            kd = has_prev ? (kappa - ka_prev) : 0.0;   // np.append([0], np.diff(kappa_gl))
-            th_prev = th_gl;
-            ka_prev = kappa;
-        }
-#endif
         // running sums of the two default reductions (velocity_offset :120-130, distance_to_reference_path :154-169)
         if (i >= half && i < Nt - 1) vo_sum += fabs(vi - A.v_des);
         dr_sum += fabs(di);
@@ -625,22 +525,6 @@ __device__ __forceinline__ FrxLaneOut frx_candidate(const FrxKernelArgs& A, cons
                     x_n = __ldcg(q + Np); y_n = __ldcg(q + Np + fstride);
                     if (need_col) th_n = __ldcg(q + Np + 2 * fstride);
                 }
-#if FRX_OPT_OBS_PREFETCH
-                // the records of the NEXT step go to L1 now (warp-uniform addresses: one request per 128-byte line), so
-                // the loops of the next iteration hit L1 instead of waiting for L2 on every group of loads
-                if (OBS && i + 1 < i1) {
-                    if (need_pred) {
-                        const char* pf = reinterpret_cast<const char*>(A.opred + (size_t)i * A.O * 8);
-                        const int nb = __ldg(A.on_pred + i) * 64;
-                        for (int b = 0; b < nb; b += 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(pf + b));
-                    }
-                    if (need_col && i >= 1) {
-                        const char* pf = reinterpret_cast<const char*>(A.ohull + (size_t)(i - 1) * A.O * 8);
-                        const int nb = __ldg(A.on_hull + (i - 1)) * 64;
-                        for (int b = 0; b < nb; b += 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(pf + b));
-                    }
-                }
-#endif
                 if (need_pred && i >= 1) {
                     // the obstacles predicted at this step: 64-byte records, warp-uniform 16-byte loads
                     const int n = __ldg(A.on_pred + (i - 1));
