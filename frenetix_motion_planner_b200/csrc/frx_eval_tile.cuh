@@ -405,7 +405,7 @@ __device__ __forceinline__ FrxLaneOut frx_candidate(const FrxKernelArgs& A, cons
         // running sums of the two default reductions (velocity_offset :120-130, distance_to_reference_path :154-169)
         if (i >= half && i < Nt - 1) vo_sum += fabs(vi - A.v_des);
         dr_sum += fabs(di);
-        if (i == Nt - 1) { v_last = vi; dr_last = di; }
+        v_last = vi; dr_last = di;       // what is left after the loop are the values of the segment's last step (Nt - 1 for its owner)
         if (XCOST) {
             S_acc.add(i, nA, nbA, ai * ai, alpha, beta, eta);
             S_len.add(i, nA, nbA, vi, alpha, beta, eta);
@@ -736,6 +736,11 @@ __device__ __forceinline__ void frx_tile_body(const FrxKernelArgs& A, const int 
     }
     for (int k = threadIdx.x; k < FRX_MAX_T_VALUES; k += FRX_THREADS)
         s_Ttab[k] = (k < A.nT) ? A.Ttab[k] : __longlong_as_double(0x7ff8000000000000LL);
+    {   // the time-power tables are read by the first memo fill a few microseconds from now: start pulling them into L2
+        const char* tp = reinterpret_cast<const char*>(A.tpow);
+        const int lines = (A.nT * 5 * TP * (int)sizeof(double) + 127) / 128;
+        for (int k = threadIdx.x; k < lines; k += FRX_THREADS) asm volatile("prefetch.global.L2 [%0];" ::"l"(tp + (size_t)k * 128));
+    }
     if (lane < FRX_MEMO_SLOTS) s_hdr[wib * FRX_MEMO_SLOTS + lane].valid = 0;
     __shared__ unsigned int s_cnt[CNT_REASON1 + 10];     // per-CTA event counters
     __shared__ unsigned long long s_part[FRX_THREADS];   // last CTA: partial counter sums
