@@ -359,7 +359,7 @@ static int prepare_plan(frx_ctx* ctx, long long N, const double* d_sampling, boo
     if (xcl) for (int k = 0; k < 6; ++k) a.xcl[k] = xcl[k];
     a.row_first = row_first; a.row_base = row_base; a.N = N;
     a.states = ctx->states.p; a.costs = ctx->costs.p; a.total = ctx->total.p; a.flags = ctx->flags.p;
-    a.seg = seg; a.Np = Np; a.keep_xyt = (!p.store_states && need_xyt) ? 1 : 0;
+    a.seg = seg; a.Np = Np; a.nf_store = p.store_states ? FRX_NUM_FIELDS : 3; a.keep_xyt = (!p.store_states && need_xyt) ? 1 : 0;
     a.traj_len = ctx->traj_len.p; a.blockbest = ctx->blockbest.p; a.blockcnt = ctx->blockcnt.p; a.counters = ctx->counters.p;
     a.winner = ctx->winner.p; a.host_res = ctx->d_res; a.n_cta = grid;
     if (ctx->counters_dirty) {

@@ -46,6 +46,12 @@ struct FrxHostResult {
     double winner_states[FRX_NUM_FIELDS][64];   // the selected candidate's state rows (Nt <= 64 samples each)
 };
 
+// state tensor index: blocks of 32 candidates, [block][step][field][32] (nf = fields stored per step: 14, or 3 when only
+// x, y, theta are kept for the obstacle pass)
+__host__ __device__ inline size_t frx_state_index(long long row, int Nt, int nf, int f, int i) {
+    return (((size_t)(row >> 5) * (size_t)Nt + (size_t)i) * (size_t)nf + (size_t)f) * 32 + (size_t)(row & 31);
+}
+
 struct FrxKernelArgs {
     // ---- scalars (frx_params, pre-digested on the host)
     double dt, a_max, v_switch, kappa_max, wb_rear, half_len, half_wid, x0_orientation, v_des;
@@ -85,8 +91,9 @@ struct FrxKernelArgs {
     long long row_base;     // added to the local index when reporting argmin
     long long N;
     // ---- outputs
-    double* states;         // [14][Nt][Np]: field, step, candidate (candidate fastest, Np = N rounded up to 32)
-    long long Np;
+    double* states;         // [Np / 32][Nt][nf_store][32]: block of 32 candidates, step, field, candidate (frx_state_index)
+    long long Np;           // N rounded up to 32
+    int nf_store;           // fields stored per step: 14 (store_states) or 3 (x, y, theta only)
     int seg;                // lanes per candidate (1, 2 or 4): which kernel instance runs, tile = 32 / seg rows
     int defer_obs;          // 1: the eval kernel skips the obstacle pass, arg-min and result record; frx_obstacle_kernel
                             //    (launched right behind it) does them

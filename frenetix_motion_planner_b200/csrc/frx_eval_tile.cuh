@@ -12,8 +12,9 @@
 //     per-thread scalar code (useful work in all 32 lanes), the time-step loop runs sequentially in each thread --
 //     time-coupled quantities (yaw rate, curvature rate, stand-still heading carry) are plain registers, no
 //     shuffles, ballots or warp-synchronous code inside the loop, so lanes may diverge freely;
-//   * the state tensor is laid out [field][step][candidate]: at every step the 32 lanes of a warp write 32
-//     consecutive candidates of one field = one fully coalesced 256-byte store;
+//   * the state tensor is laid out in blocks of 32 candidates, [block][step][field][32]: at every step the 32 lanes of a
+//     warp write 32 consecutive candidates of one field = one fully coalesced 256-byte store, and the 14 fields of the
+//     step are one contiguous 3.5 KB span (base pointer + immediate offsets);
 //   * everything that depends on the longitudinal motion s(t) only (quartic, samples, reference segment, lambda,
 //     interpolated heading/curvature, foot point, normal, time-power row) is shared by all candidates with the same
 //     (t1, s0, ss0, sss0, ss1): the warp computes it cooperatively ONCE per key (lane = time step, the reference
@@ -217,7 +218,6 @@ __device__ __forceinline__ FrxLaneOut frx_candidate(const FrxKernelArgs& A, cons
     FrxLaneOut out;
     out.ev = 0; out.total = 0.0; out.winner_ok = false; out.t_missing = false;
     const int Nt = A.Nt, TP = A.tpitch;
-    const long long Np = A.Np;
     const double dT = A.dt;
     const bool low = A.low != 0, draw = A.draw != 0, debug = A.debug != 0;
     const bool brk = !draw && !debug;
@@ -296,8 +296,11 @@ __device__ __forceinline__ FrxLaneOut frx_candidate(const FrxKernelArgs& A, cons
     }
     double vo_sum = 0.0, v_last = 0.0, dr_sum = 0.0, dr_last = 0.0;
     const int half = Nt / 2;
-    const size_t fstride = (size_t)Nt * (size_t)Np;
-    double* sp = A.states + r;
+    // state tensor: blocks of 32 candidates, [block][step][field][32] -- the 14 fields of a step are 14 consecutive
+    // 256-byte rows, so a warp's stores of one step are one 3.5 KB span addressed as base + immediate
+    constexpr size_t fstride = 32;                                   // doubles between two fields of the same step
+    const size_t sstride = (size_t)A.nf_store * 32;                  // doubles between two steps
+    double* sp = A.states + (size_t)(r >> 5) * (size_t)Nt * sstride + (size_t)(r & 31);
     const bool st_all = A.store_states != 0;
     const bool st_xyt = st_all || A.keep_xyt;
     // Simpson-rule terms
@@ -417,23 +420,14 @@ __device__ __forceinline__ FrxLaneOut frx_candidate(const FrxKernelArgs& A, cons
             a_prev = ai; thc_prev = th_cl;
         }
         // the 14 fields of this step: lanes = 32 consecutive candidates -> one coalesced 256-byte store each
-        double* p = sp + (size_t)i * (size_t)Np;
+        double* p = sp + (size_t)i * sstride;
         if (st_xyt) {           // x, y, theta are re-read by the obstacle pass: keep them in L2
             __stcg(p, xi); __stcg(p + fstride, yi); __stcg(p + 2 * fstride, th_gl);
         }
         if (st_all) {
-            p += 3 * fstride;
-            __stcs(p, vi); p += fstride;
-            __stcs(p, ai); p += fstride;
-            __stcs(p, kappa); p += fstride;
-            __stcs(p, kd); p += fstride;
-            __stcs(p, si); p += fstride;
-            __stcs(p, di); p += fstride;
-            __stcs(p, th_cl); p += fstride;
-            __stcs(p, sdi); p += fstride;
-            __stcs(p, sddi); p += fstride;
-            __stcs(p, ddi); p += fstride;
-            __stcs(p, dddi);
+            __stcs(p + 3 * fstride, vi); __stcs(p + 4 * fstride, ai); __stcs(p + 5 * fstride, kappa); __stcs(p + 6 * fstride, kd);
+            __stcs(p + 7 * fstride, si); __stcs(p + 8 * fstride, di); __stcs(p + 9 * fstride, th_cl); __stcs(p + 10 * fstride, sdi);
+            __stcs(p + 11 * fstride, sddi); __stcs(p + 12 * fstride, ddi); __stcs(p + 13 * fstride, dddi);
         }
     }
     if (SEG > 1) {
@@ -444,7 +438,7 @@ __device__ __forceinline__ FrxLaneOut frx_candidate(const FrxKernelArgs& A, cons
             if (fabs(ddivc(rint(yaw_rate * 100000.0), 100000.0, 1e-5)) > A.kappa_max * vi_first) g_first |= 4u;
             double kappa_dot = ddivc(ka_first - ka_in, dT, A.inv_dt);
             if (fabs(kappa_dot) > 0.4) g_first |= 8u;
-            if (st_all) __stcs(sp + (size_t)FRX_F_KAPPA_DOT * fstride + (size_t)i0 * (size_t)Np, ka_first - ka_in);
+            if (st_all) __stcs(sp + (size_t)FRX_F_KAPPA_DOT * fstride + (size_t)i0 * sstride, ka_first - ka_in);
         }
         if (XCOST) {
             const double a_in = __shfl_up_sync(pass, a_prev, C), thc_in = __shfl_up_sync(pass, thc_prev, C);
@@ -510,20 +504,20 @@ __device__ __forceinline__ FrxLaneOut frx_candidate(const FrxKernelArgs& A, cons
         if ((need_pred || need_d2o || need_col) && !A.defer_obs) {      // deferred: frx_obstacle_kernel does this pass
             double pbx = 0, pby = 0, pux = 0, puy = 0;   // ego box of the previous step
             if (SEG > 1 && need_col && i0 >= 1 && i0 < i1) {      // ... which another lane wrote for a later segment
-                const double* qp = sp + (size_t)(i0 - 1) * (size_t)Np;
+                const double* qp = sp + (size_t)(i0 - 1) * sstride;
                 double sn, cs;
                 sincos(__ldcg(qp + 2 * fstride), &sn, &cs);
                 pbx = __ldcg(qp) + A.wb_rear * cs; pby = __ldcg(qp + fstride) + A.wb_rear * sn; pux = cs; puy = sn;
             }
             // x, y, theta of the candidate come back from the state tensor (L2), loaded ONE STEP AHEAD of their use
-            const double* q = sp + (size_t)i0 * (size_t)Np;
+            const double* q = sp + (size_t)i0 * sstride;
             double x_n = 0.0, y_n = 0.0, th_n = 0.0;
             if (i0 < i1) { x_n = __ldcg(q); y_n = __ldcg(q + fstride); if (need_col) th_n = __ldcg(q + 2 * fstride); }
-            for (int i = i0; i < i1; ++i, q += Np) {
+            for (int i = i0; i < i1; ++i, q += sstride) {
                 const double x = x_n, y = y_n, th = th_n;
                 if (i + 1 < i1) {
-                    x_n = __ldcg(q + Np); y_n = __ldcg(q + Np + fstride);
-                    if (need_col) th_n = __ldcg(q + Np + 2 * fstride);
+                    x_n = __ldcg(q + sstride); y_n = __ldcg(q + sstride + fstride);
+                    if (need_col) th_n = __ldcg(q + sstride + 2 * fstride);
                 }
                 if (need_pred && i >= 1) {
                     // the obstacles predicted at this step: 64-byte records, warp-uniform 16-byte loads
@@ -991,7 +985,7 @@ __device__ __forceinline__ void frx_tile_body(const FrxKernelArgs& A, const int 
                 const int Nt = A.Nt;
                 for (int q = threadIdx.x; q < FRX_NUM_FIELDS * Nt; q += FRX_THREADS) {
                     const int f = q / Nt, i = q - f * Nt;
-                    A.host_res->winner_states[f][i] = __ldcg(A.states + ((size_t)f * Nt + i) * (size_t)A.Np + wi);
+                    A.host_res->winner_states[f][i] = __ldcg(A.states + frx_state_index(wi, Nt, FRX_NUM_FIELDS, f, i));
                 }
             }
         }

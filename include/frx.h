@@ -62,8 +62,8 @@ extern "C" {
 #define FRX_ERR_UNSUPPORTED (-4)
 
 /* state tensor fields.  Read-back (frx_get_states*, frx_winner_states) delivers out[field][candidate][step] with step
- * pitch frx_state_pitch(); in HBM the tensor is laid out [field][step][candidate] (candidate fastest, padded to a
- * multiple of 32) so that the 32 candidates of a warp store 256 contiguous bytes per field and step. */
+ * pitch frx_state_pitch(); in HBM the tensor is laid out in blocks of 32 candidates, [block][step][field][32], so that the
+ * 32 candidates of a warp store the 14 fields of a step as one contiguous 3.5 KB span (14 coalesced 256-byte rows). */
 enum {
     FRX_F_X = 0, FRX_F_Y, FRX_F_THETA, FRX_F_V, FRX_F_A, FRX_F_KAPPA, FRX_F_KAPPA_DOT,
     FRX_F_S, FRX_F_D, FRX_F_THETA_CL, FRX_F_S_DOT, FRX_F_S_DDOT, FRX_F_D_DOT, FRX_F_D_DDOT,
@@ -103,7 +103,7 @@ typedef struct frx_params {
     int32_t n_costs;                       /* active cost terms, name-sorted */
     int32_t cost_ids[FRX_MAX_COSTS];       /* FRX_COST_* */
     double cost_weights[FRX_MAX_COSTS];
-    int32_t store_states;    /* 1: materialise the 14 state planes [14][Nt][N] in HBM (default) */
+    int32_t store_states;    /* 1: materialise the 14 state fields of every candidate and step in HBM (default) */
     int32_t check_collisions;/* 1: OBB sweep vs predictions / static boxes for every candidate */
 } frx_params;
 
@@ -182,8 +182,8 @@ int frx_get_flags(frx_ctx* ctx, int64_t first, int64_t count, uint32_t* flags, i
  * host-side copy -- no device round trip (reference: the optimal trajectory handed back by plan(),
  * frenetix_motion_planner/reactive_planner.py:89-94) */
 int frx_winner_states(frx_ctx* ctx, uint32_t field_mask, double* out);
-/* raw device pointers of the last plan for zero-copy consumers: states [14][Nt][Np] (Np = N rounded up to 32),
- * costs [N][n_costs], total [N], flags [N] */
+/* raw device pointers of the last plan for zero-copy consumers: states [ceil(N / 32)][Nt][14][32] (element (field f,
+ * step i) of candidate r at (((r / 32) * Nt + i) * 14 + f) * 32 + r % 32), costs [N][n_costs], total [N], flags [N] */
 int frx_device_pointers(frx_ctx* ctx, void** states, void** costs, void** total, void** flags);
 /* device address of the 16-byte winner record {double min_cost; int64 global_row} of the last plan:
  * the payload of the multi-GPU arg-min exchange (all-gather of 16 B per rank, no host round trip) */
