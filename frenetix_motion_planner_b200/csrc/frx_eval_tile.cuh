@@ -83,6 +83,7 @@ struct FrxSimpson {
 // :457-460, :536-547; polynomial_trajectory.py:452-488 (quartic, closed form)
 // ------------------------------------------------------------------------------------------------------------
 __device__ __noinline__ void frx_memo_fill(const FrxKernelArgs& A, const double* __restrict__ s_ref, const double* __restrict__ s_Ttab,
+                                           const int* __restrict__ s_Tlen,
                                            double* __restrict__ mt, FrxMemoHdr* __restrict__ hdr, const double T, const double s0,
                                            const double ss0, const double sss0, const double ss1) {
     const int lane = threadIdx.x & 31;
@@ -112,7 +113,8 @@ __device__ __noinline__ void frx_memo_fill(const FrxKernelArgs& A, const double*
         __syncwarp();
         return;
     }
-    const int traj_len = __ldg(A.Tlen + tix);
+    const int traj_len = s_Tlen[tix];      // (shared memory: a global load here would put a second round trip in front of
+                                           // the loads at index traj_len - 1 below)
     const double* __restrict__ tp = A.tpow + (size_t)tix * 5 * TP;
     Poly L;
     {
@@ -730,6 +732,8 @@ __device__ __forceinline__ void frx_tile_body(const FrxKernelArgs& A, const int 
     }
     for (int k = threadIdx.x; k < FRX_MAX_T_VALUES; k += FRX_THREADS)
         s_Ttab[k] = (k < A.nT) ? A.Ttab[k] : __longlong_as_double(0x7ff8000000000000LL);
+    __shared__ int s_Tlen[FRX_MAX_T_VALUES];
+    for (int k = threadIdx.x; k < FRX_MAX_T_VALUES; k += FRX_THREADS) s_Tlen[k] = (k < A.nT) ? A.Tlen[k] : 0;
     {   // the time-power tables are read by the first memo fill a few microseconds from now: start pulling them into L2
         const char* tp = reinterpret_cast<const char*>(A.tpow);
         const int lines = (A.nT * 5 * TP * (int)sizeof(double) + 127) / 128;
@@ -849,11 +853,11 @@ __device__ __forceinline__ void frx_tile_body(const FrxKernelArgs& A, const int 
             }
             if (sa < 0) {
                 sa = (sb == 0) ? 1 : 0;
-                frx_memo_fill(A, s_ref, s_Ttab, memo + (size_t)sa * M_FIELDS * TP, hdr + sa, aT, as0, ass0, asss0, ass1);
+                frx_memo_fill(A, s_ref, s_Ttab, s_Tlen, memo + (size_t)sa * M_FIELDS * TP, hdr + sa, aT, as0, ass0, asss0, ass1);
             }
             if (mB && sb < 0) {
                 sb = 1 - sa;
-                frx_memo_fill(A, s_ref, s_Ttab, memo + (size_t)sb * M_FIELDS * TP, hdr + sb, bT, bs0, bss0, bsss0, bss1);
+                frx_memo_fill(A, s_ref, s_Ttab, s_Tlen, memo + (size_t)sb * M_FIELDS * TP, hdr + sb, bT, bs0, bss0, bsss0, bss1);
             }
             __syncwarp();
             FRX_STAMP(3);                                                    // memo slots ready
