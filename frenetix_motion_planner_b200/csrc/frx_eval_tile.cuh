@@ -316,11 +316,10 @@ __device__ __forceinline__ FrxLaneOut frx_candidate(const FrxKernelArgs& A, cons
     const int nD = Nt - 1, nbD = (nD & 1) ? nD : (nD - 1);        // integrands built from np.diff
 
     for (int i = i0; i < i1; ++i) {
-        // ---- the common case as ONE straight-line block (selects, no branches), so that the independent fp64 chains
-        // (the two slope divisions, atan, the reciprocal square root, the 1/qc refinement, the a_max(v) quotient) overlap
-        // instead of running one after the other behind reconvergence points; the rare cases -- stand-still step in
-        // high-velocity mode, a divisor outside the fast reciprocal's range -- are detected and the step is redone by
-        // the exact general code below.  Same operations, same bits in the common case.
+        // ---- straight-line code with selects instead of branches wherever the two sides are cheap, so that the
+        // independent fp64 chains (the two slope divisions, the reciprocal square root, the 1/qc refinement, the a_max(v)
+        // quotient) are scheduled together; the unchecked reciprocal sequences are bit-identical to IEEE division inside
+        // their range, a divisor outside it is detected and redone with IEEE division.
         const double si = mt[M_S * TP + i], sdi = mt[M_SD * TP + i], sddi = mt[M_SDD * TP + i];
         const double interp = mt[M_INTERP * TP + i];
         const double k_r = mt[M_KR * TP + i], k_r_d = mt[M_KRD * TP + i];
@@ -346,34 +345,38 @@ __device__ __forceinline__ FrxLaneOut frx_candidate(const FrxKernelArgs& A, cons
             dp = low ? ddi : dph;
             dpp = low ? dddi : (mov ? qb : 0.);
         }
-        double th_cl = datan(dp);                     // np.arctan2(dp, 1.0)
-        double th_gl = th_cl + interp;
+        // :423-454 orientations.  Which steps stand still depends on s(t) only, so `direct` is uniform over the lanes of a
+        // memo slot: the branch below costs (almost) no divergence, and a stand-still step runs the trigonometric version
+        // INSTEAD of the algebraic one (tiles of stopping candidates were the kernel's 20 % slower tail when both ran).
         const double oneKrD = 1 - k_r * di;
-        const double w = 1.0 + dp * dp;
-        double cosT = drsqrt_ge1(w), secT = w * cosT, tanT = dp;
-        double qc = oneKrD * secT;
-        double cq = drcp_unchecked(qc);
+        double th_cl, th_gl, cosT, secT, tanT;
+        if (direct || !evaluate) {
+            th_cl = datan(dp);                        // np.arctan2(dp, 1.0)
+            th_gl = th_cl + interp;
+            // cos, tan and 1/cos of theta_cl = atan(dp): with w = 1 + dp^2, cos = 1/sqrt(w), 1/cos = sqrt(w), tan = dp hold
+            // algebraically (same <= 1-2 ulp error class as libm's cos/tan of the rounded angle)
+            const double w = 1.0 + dp * dp;
+            cosT = drsqrt_ge1(w); secT = w * cosT; tanT = dp;
+        } else {
+            // stand-still in high-velocity mode keeps the previous global orientation and needs real trigonometry
+            th_gl = th_prev; th_cl = th_gl - interp;
+            double sT;
+            sincos(th_cl, &sT, &cosT);
+            secT = ddivg(1.0, cosT);
+            tanT = sT * secT;
+        }
+        // :457-478
+        double qc = oneKrD * secT;                    // oneKrD / cos(theta_cl)
+        double cq = drcp_unchecked(qc);               // cos(theta_cl) / oneKrD
         double kappa = (dpp + (k_r * dp + k_r_d * di) * tanT) * cosT * (cq * cq) + cq * k_r;
         double vi = sdi * qc;
         double ai = sddi * qc + ((sdi * sdi) * secT) * (oneKrD * tanT * (kappa * qc - k_r) - (k_r_d * di + k_r * dp));
         const double a_q = ddivf(A.a_max * A.v_switch, vi);
         double a_hi = (vi > A.v_switch) ? a_q : A.a_max;
-        if (evaluate && (!direct || !drcp_in_range(qc) || ((vi > A.v_switch) && !drcp_in_range(vi)))) {
-            // ---- the general path (:423-478): stand-still keeps the previous global orientation and needs real
-            // trigonometry; degenerate divisors go through IEEE division
-            if (!direct) { th_gl = th_prev; th_cl = th_gl - interp; }
-            if (direct) {
-                cosT = rsqrt(w); secT = w * cosT; tanT = dp;
-            } else {
-                double sT;
-                sincos(th_cl, &sT, &cosT);
-                secT = ddivg(1.0, cosT);
-                tanT = sT * secT;
-            }
-            qc = oneKrD * secT;
+        if (evaluate && (!drcp_in_range(qc) || ((vi > A.v_switch) && !drcp_in_range(vi)))) {
+            // a divisor outside the fast reciprocal's range: IEEE division
             cq = ddivg(1.0, qc);
             kappa = (dpp + (k_r * dp + k_r_d * di) * tanT) * cosT * (cq * cq) + cq * k_r;
-            vi = sdi * qc;
             ai = sddi * qc + ((sdi * sdi) * secT) * (oneKrD * tanT * (kappa * qc - k_r) - (k_r_d * di + k_r * dp));
             a_hi = (vi > A.v_switch) ? ddivg(A.a_max * A.v_switch, vi) : A.a_max;
         }
