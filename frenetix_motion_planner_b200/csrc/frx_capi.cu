@@ -439,7 +439,7 @@ static int enqueue_plan(frx_ctx* ctx, long long N, const double* d_sampling, boo
     ctx->counters_dirty = true;          // cleared again once the launch sequence has completed
 #ifdef FRX_TRACE
     static DevBuf<unsigned long long> trace;
-    const size_t n_tr = (size_t)grid * FRX_WARPS_PER_CTA * 8;
+    const size_t n_tr = (size_t)grid * FRX_WARPS_PER_CTA * 16;
     CK(trace.reserve(n_tr));
     CK(cudaMemsetAsync(trace.p, 0, n_tr * 8, st));
     a.trace = trace.p;

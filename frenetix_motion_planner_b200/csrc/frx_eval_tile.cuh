@@ -37,9 +37,14 @@ __device__ __forceinline__ unsigned long long frx_now() {
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     return t;
 }
-#define FRX_STAMP(k) do { if (A.trace && lane == 0 && !traced) A.trace[((size_t)cta_local * FRX_WARPS_PER_CTA + wib) * 8 + (k)] = frx_now(); } while (0)
+#define FRX_STAMP(k) do { if (A.trace && lane == 0 && !traced) A.trace[((size_t)cta_local * FRX_WARPS_PER_CTA + wib) * 16 + (k)] = frx_now(); } while (0)
 #else
 #define FRX_STAMP(k) do { } while (0)
+#endif
+#if FRX_TRACE
+#define FRX_TRW ((A.trace && !traced) ? A.trace + ((size_t)cta_local * FRX_WARPS_PER_CTA + wib) * 16 : nullptr)
+#else
+#define FRX_TRW nullptr
 #endif
 
 enum { M_S = 0, M_SD, M_SDD, M_INTERP, M_KR, M_KRD, M_PX, M_PY, M_SN, M_CS, M_T1, M_T2, M_T3, M_T4, M_T5, M_FIELDS };
@@ -83,7 +88,7 @@ struct FrxSimpson {
 // :457-460, :536-547; polynomial_trajectory.py:452-488 (quartic, closed form)
 // ------------------------------------------------------------------------------------------------------------
 __device__ __noinline__ void frx_memo_fill(const FrxKernelArgs& A, const double* __restrict__ s_ref, const double* __restrict__ s_Ttab,
-                                           const int* __restrict__ s_Tlen,
+                                           const int* __restrict__ s_Tlen, unsigned long long* trw,
                                            double* __restrict__ mt, FrxMemoHdr* __restrict__ hdr, const double T, const double s0,
                                            const double ss0, const double sss0, const double ss1) {
     const int lane = threadIdx.x & 31;
@@ -102,6 +107,12 @@ __device__ __noinline__ void frx_memo_fill(const FrxKernelArgs& A, const double*
         hdr->key[0] = T; hdr->key[1] = s0; hdr->key[2] = ss0; hdr->key[3] = sss0; hdr->key[4] = ss1;
         hdr->valid = 1;
     }
+#if FRX_TRACE
+#define FRX_MSTAMP(k) do { if (trw && lane == 0) trw[k] = frx_now(); } while (0)
+#else
+#define FRX_MSTAMP(k) do { } while (0)
+#endif
+    FRX_MSTAMP(8);
     // ---------------- time table of this duration (reactive_planner.py:296-303)
     int tix = -1;
     for (int b0 = 0; b0 < A.nT; b0 += 32) {
@@ -136,6 +147,7 @@ __device__ __noinline__ void frx_memo_fill(const FrxKernelArgs& A, const double*
         sd_last = poly_vel(L, tl, tl2, tl3, tl4);
         s_inc = dT * sd_last;
     }
+    FRX_MSTAMP(9);       // coefficients, s_first, s_last (time-table loads) done
     bool any_neg = false, any_acc = false;
     int first_none = Nt;
     for (int c0 = 0; c0 < TP; c0 += 32) {
@@ -157,12 +169,14 @@ __device__ __noinline__ void frx_memo_fill(const FrxKernelArgs& A, const double*
             for (int k = il; k < i; ++k) vs += s_inc;
             vsd = sd_last; vsdd = 0.0;
         }
+        FRX_MSTAMP(10);  // samples + extension
         any_neg |= __any_sync(FULL, act && (vsd < -FRX_EPS));
         any_acc |= __any_sync(FULL, act && (fabs(vsdd) > A.a_max));
         if (fabs(vsd) < FRX_EPS) vsd = 0.0;     // :355
         // :415-420 segment lookup (python negative-index wrap reproduced), :457-460 curvature
         int j = first_greater(rp, M, vs, pos_first, inv_step);
         int ia = (j == 0) ? (M - 1) : (j - 1);
+        FRX_MSTAMP(11);  // segment search
         double pa = rp[ia], pb = rp[j];
         double lam = ddivf(vs - pa, pb - pa);
         double tha = rth[ia], thb = rth[j];
@@ -176,8 +190,10 @@ __device__ __noinline__ void frx_memo_fill(const FrxKernelArgs& A, const double*
         double px = (1.0 - lam) * rx[ia] + lam * rx[j];
         double py = (1.0 - lam) * ry[ia] + lam * ry[j];
         double thr = tha + lam * (thb - tha);
+        FRX_MSTAMP(12);  // interpolation
         double sn, cs;
         sincos(thr, &sn, &cs);
+        FRX_MSTAMP(13);  // sincos
         mt[M_S * TP + i] = vs; mt[M_SD * TP + i] = vsd; mt[M_SDD * TP + i] = vsdd;
         mt[M_INTERP * TP + i] = interp;
         mt[M_KR * TP + i] = k_r; mt[M_KRD * TP + i] = k_r_d;
@@ -195,6 +211,7 @@ __device__ __noinline__ void frx_memo_fill(const FrxKernelArgs& A, const double*
         hdr->goal = poly_pos(L, T, t2, t3, t4, t5) - s0;
     }
     __syncwarp();
+    FRX_MSTAMP(14);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -856,11 +873,11 @@ __device__ __forceinline__ void frx_tile_body(const FrxKernelArgs& A, const int 
             }
             if (sa < 0) {
                 sa = (sb == 0) ? 1 : 0;
-                frx_memo_fill(A, s_ref, s_Ttab, s_Tlen, memo + (size_t)sa * M_FIELDS * TP, hdr + sa, aT, as0, ass0, asss0, ass1);
+                frx_memo_fill(A, s_ref, s_Ttab, s_Tlen, FRX_TRW, memo + (size_t)sa * M_FIELDS * TP, hdr + sa, aT, as0, ass0, asss0, ass1);
             }
             if (mB && sb < 0) {
                 sb = 1 - sa;
-                frx_memo_fill(A, s_ref, s_Ttab, s_Tlen, memo + (size_t)sb * M_FIELDS * TP, hdr + sb, bT, bs0, bss0, bsss0, bss1);
+                frx_memo_fill(A, s_ref, s_Ttab, s_Tlen, nullptr, memo + (size_t)sb * M_FIELDS * TP, hdr + sb, bT, bs0, bss0, bsss0, bss1);
             }
             __syncwarp();
             FRX_STAMP(3);                                                    // memo slots ready
