@@ -16,6 +16,7 @@ print("median durations: prologue %.1f | rows %.1f | memo fill(s) %.1f | candida
 
 if (t[:, 8:15] > 0).any():
     m = t[(t[:, 8] > 0) & (t[:, 14] > 0)]
-    lab = ["call -> table lookup", "coefficients + time-table loads", "samples + extension", "segment search", "interpolation", "sincos", "stores + header"]
+    lab = ["table lookup + coefficients + first time-table loads", "per-lane time-table loads + samples + extension",
+           "votes + segment search", "interpolation", "sincos", "stores + header"]
     print("first memo fill, median us per phase:", ", ".join(f"{lab[k]} {np.median(m[:, 9 + k] - m[:, 8 + k]) / 1e3:.2f}" for k in range(6)),
           f"| total {np.median(m[:, 14] - m[:, 8]) / 1e3:.2f}")
