@@ -69,7 +69,7 @@ struct frx_ctx {
     bool have_params = false, have_ref = false, have_tables = false;
     double kappa_max = 0.0;
 
-    DevBuf<double> ref; int M = 0, Mpad = 0;
+    DevBuf<double> ref; int M = 0, Mpad = 0; double inv_step = 0.0;
     DevBuf<double> Ttab; DevBuf<int> Tlen; DevBuf<double> tpow; int nT = 0, tpitch = 0;
     DevBuf<double> opred, ohull; DevBuf<int> on_pred, on_hull; int compact_Nt = 0;
     DevBuf<double> obs, raw_pos, raw_cov, raw_theta, raw_hl, raw_hw; DevBuf<int> obs_len; int O = 0, T = 0, Tp = 0;
@@ -197,6 +197,7 @@ int frx_set_reference(frx_ctx* ctx, int32_t M, const double* ref_pos, const doub
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaMemcpy(ctx->ref.p, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
     ctx->M = M; ctx->Mpad = Mpad; ctx->have_ref = true;
+    ctx->inv_step = (double)(M - 1) / (ref_pos[M - 1] - ref_pos[0]);
     return FRX_OK;
 }
 
@@ -344,7 +345,7 @@ static int prepare_plan(frx_ctx* ctx, long long N, const double* d_sampling, boo
     FrxKernelArgs a;
     memset(&a, 0, sizeof(a));
     a.dt = p.dt; a.a_max = p.a_max; a.v_switch = p.v_switch; a.kappa_max = ctx->kappa_max; a.wb_rear = p.wb_rear_axle;
-    a.inv_dt = 1.0 / p.dt; a.inv_Nt = 1.0 / (double)Nt;
+    a.inv_dt = 1.0 / p.dt; a.inv_Nt = 1.0 / (double)Nt; a.inv_step = ctx->inv_step;
     a.half_len = p.length / 2; a.half_wid = p.width / 2; a.x0_orientation = p.x0_orientation; a.v_des = p.desired_velocity;
     for (int k = 0; k < K; ++k) { a.w[k] = p.cost_weights[k]; a.cost_ids[k] = p.cost_ids[k]; }
     a.n_costs = K; a.Nt = Nt; a.Ntp = Ntp; a.low = p.low_vel_mode; a.draw = p.draw_traj_set; a.debug = p.kinematic_debug;

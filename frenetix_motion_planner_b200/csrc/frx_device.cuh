@@ -56,6 +56,7 @@ struct FrxKernelArgs {
     // ---- scalars (frx_params, pre-digested on the host)
     double dt, a_max, v_switch, kappa_max, wb_rear, half_len, half_wid, x0_orientation, v_des;
     double inv_dt, inv_Nt;  // correctly rounded 1/dt and 1/Nt (host), for ddivc
+    double inv_step;        // (M - 1) / (ref_pos[M-1] - ref_pos[0]): initial guess of the reference-segment search
     double w[FRX_MAX_COSTS];
     int cost_ids[FRX_MAX_COSTS];
     int n_costs;

@@ -101,7 +101,7 @@ __device__ __noinline__ void frx_memo_fill(const FrxKernelArgs& A, const double*
     const double* __restrict__ ry = s_ref + 5 * Mpad;
     const double dT = A.dt;
     const double pos_first = rp[0], pos_last = rp[M - 1];
-    const double inv_step = (double)(M - 1) / (pos_last - pos_first);
+    const double inv_step = A.inv_step;       // (M - 1) / (pos_last - pos_first), computed by the host with the same IEEE operations
     __syncwarp();
     if (lane == 0) {
         hdr->key[0] = T; hdr->key[1] = s0; hdr->key[2] = ss0; hdr->key[3] = sss0; hdr->key[4] = ss1;
@@ -138,11 +138,20 @@ __device__ __noinline__ void frx_memo_fill(const FrxKernelArgs& A, const double*
         L.c5 = 0.0;
     }
     const int il = traj_len - 1;
+    // the time-power rows of this duration go into the memo first (the lateral pass re-reads them): ONE round of global
+    // loads for the whole fill -- the entries at step 0 and step traj_len - 1 needed next are then read from shared memory
+    for (int c0 = 0; c0 < TP; c0 += 32) {
+        const int i = c0 + lane;
+        const double t = __ldg(tp + i), t2 = __ldg(tp + TP + i), t3 = __ldg(tp + 2 * TP + i), t4 = __ldg(tp + 3 * TP + i),
+                     t5 = __ldg(tp + 4 * TP + i);
+        mt[M_T1 * TP + i] = t; mt[M_T2 * TP + i] = t2; mt[M_T3 * TP + i] = t3; mt[M_T4 * TP + i] = t4; mt[M_T5 * TP + i] = t5;
+    }
+    __syncwarp();
     double s_last = 0.0, sd_last = 0.0, s_inc = 0.0;
-    const double s_first = poly_pos(L, __ldg(tp), __ldg(tp + TP), __ldg(tp + 2 * TP), __ldg(tp + 3 * TP), __ldg(tp + 4 * TP));
+    const double s_first = poly_pos(L, mt[M_T1 * TP], mt[M_T2 * TP], mt[M_T3 * TP], mt[M_T4 * TP], mt[M_T5 * TP]);
     if (traj_len < Nt) {   // values of the last polynomial sample feed the extension of every later step
-        double tl = __ldg(tp + il), tl2 = __ldg(tp + TP + il), tl3 = __ldg(tp + 2 * TP + il), tl4 = __ldg(tp + 3 * TP + il),
-               tl5 = __ldg(tp + 4 * TP + il);
+        double tl = mt[M_T1 * TP + il], tl2 = mt[M_T2 * TP + il], tl3 = mt[M_T3 * TP + il], tl4 = mt[M_T4 * TP + il],
+               tl5 = mt[M_T5 * TP + il];
         s_last = poly_pos(L, tl, tl2, tl3, tl4, tl5);
         sd_last = poly_vel(L, tl, tl2, tl3, tl4);
         s_inc = dT * sd_last;
@@ -155,9 +164,8 @@ __device__ __noinline__ void frx_memo_fill(const FrxKernelArgs& A, const double*
         const bool act = i < Nt;
         double vs = 0, vsd = 0, vsdd = 0;
         {
-            double t = __ldg(tp + i), t2 = __ldg(tp + TP + i), t3 = __ldg(tp + 2 * TP + i), t4 = __ldg(tp + 3 * TP + i),
-                   t5 = __ldg(tp + 4 * TP + i);
-            mt[M_T1 * TP + i] = t; mt[M_T2 * TP + i] = t2; mt[M_T3 * TP + i] = t3; mt[M_T4 * TP + i] = t4; mt[M_T5 * TP + i] = t5;
+            const double t = mt[M_T1 * TP + i], t2 = mt[M_T2 * TP + i], t3 = mt[M_T3 * TP + i], t4 = mt[M_T4 * TP + i],
+                         t5 = mt[M_T5 * TP + i];
             if (i < traj_len) {
                 vs = poly_pos(L, t, t2, t3, t4, t5);
                 vsd = poly_vel(L, t, t2, t3, t4);
