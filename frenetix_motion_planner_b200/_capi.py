@@ -64,7 +64,7 @@ class FrxResult(C.Structure):
 
 EXPORTS = ("frx_abi_version", "frx_create", "frx_destroy", "frx_last_error", "frx_set_reference", "frx_set_params",
            "frx_set_time_tables", "frx_set_predictions", "frx_set_obstacle_positions", "frx_set_static_obbs",
-           "frx_plan", "frx_plan_device", "frx_plan_device_async", "frx_plan_wait", "frx_plan_grid", "frx_plan_batched", "frx_state_pitch", "frx_get_states",
+           "frx_plan", "frx_plan_device", "frx_plan_device_async", "frx_plan_wait", "frx_plan_grid", "frx_plan_batched", "frx_state_pitch", "frx_last_launches", "frx_get_states",
            "frx_get_states_range", "frx_winner_states", "frx_get_costs", "frx_get_flags", "frx_device_pointers", "frx_winner_device_pointer",
            "frx_selftest_fdiv", "frx_selftest_divc", "frx_set_stream",
            "frx_synchronize")
@@ -106,6 +106,7 @@ def load_library(path: Optional[str] = None):
                                   C.POINTER(FrxResult)]
     lib.frx_plan_batched.argtypes = [C.c_int32, C.POINTER(vp), C.POINTER(C.c_int64), C.POINTER(dp), C.POINTER(FrxResult)]
     lib.frx_state_pitch.argtypes = [vp]; lib.frx_state_pitch.restype = C.c_int32
+    lib.frx_last_launches.argtypes = [vp]; lib.frx_last_launches.restype = C.c_int32
     lib.frx_get_states.argtypes = [vp, C.c_int64, C.POINTER(C.c_int64), C.c_uint32, dp]
     lib.frx_get_states_range.argtypes = [vp, C.c_int64, C.c_int64, C.c_uint32, dp]
     lib.frx_winner_states.argtypes = [vp, C.c_uint32, dp]
@@ -118,7 +119,7 @@ def load_library(path: Optional[str] = None):
     lib.frx_set_stream.argtypes = [vp, vp]
     lib.frx_synchronize.argtypes = [vp]
     for name in EXPORTS:
-        if name not in ("frx_last_error", "frx_state_pitch", "frx_abi_version"):
+        if name not in ("frx_last_error", "frx_state_pitch", "frx_last_launches", "frx_abi_version"):
             getattr(lib, name).restype = C.c_int
     if path is None:
         _lib = lib
@@ -279,6 +280,10 @@ class Handler:
     # ---- read-back --------------------------------------------------------------------------
     def state_pitch(self) -> int:
         return int(self._lib.frx_state_pitch(self._ctx))
+
+    def last_launches(self) -> int:
+        """Kernels of the library the last plan launched."""
+        return int(self._lib.frx_last_launches(self._ctx))
 
     @staticmethod
     def _mask(fields) -> int:

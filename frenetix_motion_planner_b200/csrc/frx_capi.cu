@@ -88,6 +88,7 @@ struct frx_ctx {
 
     long long lastN = 0, lastNp = 0; int lastK = 0, lastNt = 0, lastNtp = 0;
     bool last_all_fields = false;     // the last plan materialised all 14 state planes
+    int last_launches = 0;            // kernels the last plan launched (eval, obstacle, collision counter, set-up)
     int occ_Mpad = -1, occ_nchunk = -1, occ_blocks = 1;
 };
 
@@ -379,6 +380,7 @@ static int enqueue_finish(frx_ctx* ctx, long long N, long long row_base, int gri
     (void)grid;
     const frx_params& p = ctx->prm;
     if (p.check_collisions && (ctx->O > 0 || ctx->B > 0)) {
+        ctx->last_launches += 1;
         long long cg = (N + 255) / 256;
         if (cg > (long long)ctx->sm_count * 4) cg = (long long)ctx->sm_count * 4;
         frx_launch_collision_counter(N, row_base, ctx->total.p, ctx->flags.p, ctx->winner.p, ctx->counters.p, (int)cg, st);
@@ -447,6 +449,7 @@ static int enqueue_plan(frx_ctx* ctx, long long N, const double* d_sampling, boo
 #endif
     rc = choose_obstacle_split(ctx, &a, grid);
     if (rc != FRX_OK) return rc;
+    ctx->last_launches = 1 + (a.defer_obs ? 1 : 0);
     CK(cudaEventRecord(ctx->evk0, st));
     CK(frx_launch_eval(a, nchunk, grid, st));
     if (a.defer_obs) CK(frx_launch_obstacle_pass(a, ctx->sm_count, st));
@@ -610,6 +613,7 @@ int frx_plan_batched(int32_t n_agents, frx_ctx** ctxs, const int64_t* n_rows, co
     // twice as slow -- 1.31 ms against 0.66 ms for 6 x 50,000 rows)
     CK(cudaEventRecord(ctx->evk1, st));
     for (int a = 0; a < n_agents; ++a) {
+        ctxs[a]->last_launches = (a == 0) ? 1 : 0;       // the one batched eval kernel is booked on the first context
         int rc = enqueue_finish(ctxs[a], n_rows[a], 0, grids[a], st);
         if (rc != FRX_OK) { ctx->err = ctxs[a]->err; return rc; }
     }
@@ -628,6 +632,7 @@ int frx_plan_batched(int32_t n_agents, frx_ctx** ctxs, const int64_t* n_rows, co
 }
 
 int32_t frx_state_pitch(const frx_ctx* ctx) { return ctx ? ctx->lastNtp : 0; }
+int32_t frx_last_launches(const frx_ctx* ctx) { return ctx ? ctx->last_launches : 0; }
 
 int frx_get_states(frx_ctx* ctx, int64_t n_idx, const int64_t* idx, uint32_t field_mask, double* out) {
     if (!ctx) return FRX_ERR_INVALID;

@@ -173,6 +173,9 @@ int frx_plan_batched(int32_t n_agents, frx_ctx** ctxs, const int64_t* n_rows, co
 
 /* read-back (rows are LOCAL indices of the last plan call) */
 int32_t frx_state_pitch(const frx_ctx* ctx);
+/* kernels of this library the last plan on ctx launched (eval kernel, obstacle kernel, collision counter): what a
+ * benchmark reports as its launch count */
+int32_t frx_last_launches(const frx_ctx* ctx);
 int frx_get_states(frx_ctx* ctx, int64_t n_idx, const int64_t* idx, uint32_t field_mask, double* out);
 int frx_get_states_range(frx_ctx* ctx, int64_t first, int64_t count, uint32_t field_mask, double* out);
 int frx_get_costs(frx_ctx* ctx, int64_t first, int64_t count, double* costs, double* total);
