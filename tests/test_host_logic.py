@@ -113,3 +113,66 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in txt.replace("oracle/", "").replace("the oracle", "").lower() or f == "synthetic.py", f
+
+
+def test_bundle_reads_the_selected_row_from_the_result_record():
+    """TrajectoryBundle.states_of(argmin) uses the winner rows published with the arg-min (no device gather); any other
+    row goes through the gather."""
+    from frenetix_motion_planner_b200.trajectories import TrajectoryBundle
+
+    class FakeHandler:
+        Nt = 4
+        calls = []
+
+        def winner_states(self, fields=None):
+            self.calls.append("winner")
+            return np.full((14, 4), 7.0)
+
+        def get_states(self, idx, fields=None):
+            self.calls.append(("gather", int(idx[0])))
+            return np.full((14, len(idx), 4), 3.0)
+
+    h = FakeHandler()
+    b = TrajectoryBundle(h, 10, ["lateral_jerk"], [1.0], 0.1, 0.3, 4, False, sampling=np.zeros((10, 13)))
+    assert b.winner_row is None
+    assert b.states_of(5)[0, 0] == 3.0 and h.calls[-1] == ("gather", 5)
+    b.winner_row = 5
+    assert b.states_of(5)[0, 0] == 7.0 and h.calls[-1] == "winner"
+    assert b.states_of(6)[0, 0] == 3.0 and h.calls[-1] == ("gather", 6)
+
+
+def test_state_tensor_index_is_a_bijection_onto_blocks_of_32_candidates():
+    """frx_state_index (csrc/frx_device.cuh): [block of 32 candidates][step][field][32] -- restated here, checked to be a
+    bijection onto [0, 14 * Nt * Np) with the 14 fields of one (block, step) contiguous."""
+    def index(row, Nt, nf, f, i):
+        return (((row >> 5) * Nt + i) * nf + f) * 32 + (row & 31)
+    Nt, nf, N = 5, 14, 70
+    Np = (N + 31) // 32 * 32
+    seen = set()
+    for row in range(Np):
+        for i in range(Nt):
+            for f in range(nf):
+                seen.add(index(row, Nt, nf, f, i))
+    assert seen == set(range(nf * Nt * Np))
+    base = index(37, Nt, nf, 0, 2)
+    assert [index(37, Nt, nf, f, 2) - base for f in range(nf)] == [32 * f for f in range(nf)]
+    src = open(os.path.join(ROOT, "frenetix_motion_planner_b200", "csrc", "frx_device.cuh")).read()
+    assert "(((size_t)(row >> 5) * (size_t)Nt + (size_t)i) * (size_t)nf + (size_t)f) * 32 + (size_t)(row & 31)" in src
+
+
+def test_reference_arm_prints_one_json_line_on_cpu():
+    """bench.py --impl reference runs on the host cores only (oracle port) and emits the contract's keys."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "dtype", "data",
+              "config", "cpu_baseline", "e2e", "impl"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] == 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
