@@ -159,7 +159,19 @@ class ReactivePlannerB200:
         self._ref_dirty = True
 
     def set_scenario(self, scenario):
+        """planner.py:550-565: keeps the scenario and, once, builds the road boundary from its lanelet network (here as
+        thin static boxes, road_boundary.py -- the drivability checker's triangulated boundary is not available)."""
         self.scenario = scenario
+        network = getattr(scenario, "lanelet_network", None)
+        if self.static_obbs is None and network is not None:
+            self.set_road_boundary(network)
+
+    def set_road_boundary(self, lanelets, **kw):
+        """`lanelets`: a commonroad LaneletNetwork, or the plain dict of road_boundary.lanelets_from_commonroad_xml."""
+        from . import road_boundary as rb
+        if not isinstance(lanelets, dict):
+            lanelets = rb.lanelets_from_network(lanelets)
+        self.set_static_obstacles(rb.road_boundary_obbs(lanelets, **kw))
 
     def set_static_obstacles(self, obbs):
         self.static_obbs = None if obbs is None else np.asarray(obbs, dtype=np.float64).reshape(-1, 5)
