@@ -59,14 +59,15 @@ class FrxResult(C.Structure):
     _fields_ = [("argmin", C.c_int64), ("min_cost", C.c_double), ("n_rows", C.c_int64), ("n_in_list", C.c_int64),
                 ("n_feasible", C.c_int64), ("n_candidates", C.c_int64), ("n_collide", C.c_int64),
                 ("n_boundary", C.c_int64), ("collision_counter", C.c_int64), ("reason_counts", C.c_int64 * 11),
-                ("eval_kernel_ms", C.c_float), ("total_device_ms", C.c_float)]
+                ("eval_kernel_ms", C.c_float), ("total_device_ms", C.c_float),
+                ("obstacle_kernel_ms", C.c_float), ("reserved_", C.c_float)]
 
 
 EXPORTS = ("frx_abi_version", "frx_create", "frx_destroy", "frx_last_error", "frx_set_reference", "frx_set_params",
            "frx_set_time_tables", "frx_set_predictions", "frx_set_obstacle_positions", "frx_set_static_obbs",
            "frx_plan", "frx_plan_device", "frx_plan_device_async", "frx_plan_wait", "frx_plan_grid", "frx_plan_batched", "frx_state_pitch", "frx_last_launches", "frx_get_states",
            "frx_get_states_range", "frx_winner_states", "frx_get_costs", "frx_get_flags", "frx_device_pointers", "frx_winner_device_pointer",
-           "frx_selftest_fdiv", "frx_selftest_divc", "frx_set_stream",
+           "frx_selftest_fdiv", "frx_selftest_divc", "frx_selftest_fp64_peak", "frx_set_stream",
            "frx_synchronize")
 
 _lib = None
@@ -116,6 +117,7 @@ def load_library(path: Optional[str] = None):
     lib.frx_winner_device_pointer.argtypes = [vp, C.POINTER(vp)]
     lib.frx_selftest_fdiv.argtypes = [vp, C.c_int64, dp, dp, dp, dp]
     lib.frx_selftest_divc.argtypes = [vp, C.c_int64, dp, C.c_double, dp, dp]
+    lib.frx_selftest_fp64_peak.argtypes = [vp, dp]
     lib.frx_set_stream.argtypes = [vp, vp]
     lib.frx_synchronize.argtypes = [vp]
     for name in EXPORTS:
@@ -354,6 +356,12 @@ class Handler:
         q1, q2 = np.empty_like(a), np.empty_like(a)
         self._check(self._lib.frx_selftest_divc(self._ctx, a.size, _dptr(a), float(b), _dptr(q1), _dptr(q2)))
         return q1, q2
+
+    def fp64_peak_tflops(self) -> float:
+        """Measured DFMA throughput of this GPU (2 flop per FMA), the roofline denominator of the obstacle kernel."""
+        v = C.c_double()
+        self._check(self._lib.frx_selftest_fp64_peak(self._ctx, C.byref(v)))
+        return float(v.value)
 
     def winner_device_pointer(self) -> int:
         p = C.c_void_p()

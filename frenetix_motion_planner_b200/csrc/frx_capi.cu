@@ -22,8 +22,10 @@ cudaError_t frx_launch_eval_batched(const FrxKernelArgs* h_agents, const FrxKern
 void frx_launch_obstacle_prep(int O, int T, int Tp, const double* pos, const double* cov, const double* theta,
                               const double* hl, const double* hw, double* obs, cudaStream_t st);
 void frx_launch_static_prep(int B, const double* obb, double* out, cudaStream_t st);
-void frx_launch_obstacle_compact(int O, int Tp, int Nt, const double* obs, const int* obs_len, double* pred, double* hull,
-                                 int* n_pred, int* n_hull, cudaStream_t st);
+void frx_launch_obstacle_compact(int O, int Tp, int Nt, const double* obs, const int* obs_len, double ox, double oy, double* pred,
+                                 double* hull, float4* hull32, int* n_pred, int* n_hull, cudaStream_t st);
+void frx_launch_static_cull(int B, const double* sobb, double ox, double oy, float4* out, cudaStream_t st);
+double frx_measure_fp64_peak(int sm_count, cudaStream_t st, cudaError_t* err);
 void frx_launch_collision_counter(long long N, long long row_base, const double* total, const uint32_t* flags,
                                   const FrxBest* winner, unsigned long long* counters, int grid, cudaStream_t st);
 void frx_launch_gather(const double* states, long long Np, int Nt, int Ntp, const long long* idx, long long first,
@@ -60,7 +62,8 @@ struct DevBuf {
 struct frx_ctx {
     int device = 0;
     cudaStream_t stream = nullptr, own_stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr, evkm = nullptr;
+    bool split_last = false;           // the last plan ran the obstacle pass as its own kernel (evkm lies between the two)
     std::string err;
     int sm_count = 148;
     int max_smem_optin = 0;
@@ -71,7 +74,9 @@ struct frx_ctx {
 
     DevBuf<double> ref; int M = 0, Mpad = 0; double inv_step = 0.0;
     DevBuf<double> Ttab; DevBuf<int> Tlen; DevBuf<double> tpow; int nT = 0, tpitch = 0;
-    DevBuf<double> opred, ohull; DevBuf<int> on_pred, on_hull; int compact_Nt = 0;
+    DevBuf<double> opred, ohull; DevBuf<float4> ohull32, sobb32; DevBuf<int> on_pred, on_hull; int compact_Nt = 0;
+    double origin_x = 0.0, origin_y = 0.0;     // frame of the fp32 cull records: first vertex of the reference path
+    bool sobb32_dirty = true;
     DevBuf<double> obs, raw_pos, raw_cov, raw_theta, raw_hl, raw_hw; DevBuf<int> obs_len; int O = 0, T = 0, Tp = 0;
     DevBuf<double> obs_pos; int n_obs_pos = 0;
     DevBuf<double> sobb, raw_sobb; int B = 0;
@@ -132,7 +137,7 @@ int frx_create(int device_ordinal, frx_ctx** out) {
     ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
     if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return FRX_ERR_CUDA; }
     ctx->stream = ctx->own_stream;
-    cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1); cudaEventCreate(&ctx->evk0); cudaEventCreate(&ctx->evk1);
+    cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1); cudaEventCreate(&ctx->evk0); cudaEventCreate(&ctx->evk1); cudaEventCreate(&ctx->evkm);
     if (cudaHostAlloc((void**)&ctx->h_res, sizeof(HostResult), cudaHostAllocMapped) != cudaSuccess ||
         cudaHostGetDevicePointer((void**)&ctx->d_res, ctx->h_res, 0) != cudaSuccess) {
         frx_destroy(ctx);
@@ -152,7 +157,7 @@ int frx_destroy(frx_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
     ctx->ref.release(); ctx->Ttab.release(); ctx->Tlen.release(); ctx->tpow.release();
-    ctx->opred.release(); ctx->ohull.release(); ctx->on_pred.release(); ctx->on_hull.release();
+    ctx->opred.release(); ctx->ohull.release(); ctx->ohull32.release(); ctx->sobb32.release(); ctx->on_pred.release(); ctx->on_hull.release();
     ctx->obs.release(); ctx->raw_pos.release(); ctx->raw_cov.release(); ctx->raw_theta.release();
     ctx->raw_hl.release(); ctx->raw_hw.release(); ctx->obs_len.release(); ctx->obs_pos.release();
     ctx->sobb.release(); ctx->raw_sobb.release(); ctx->sampling.release(); ctx->grid.release();
@@ -163,6 +168,7 @@ int frx_destroy(frx_ctx* ctx) {
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->evk0) cudaEventDestroy(ctx->evk0);
     if (ctx->evk1) cudaEventDestroy(ctx->evk1);
+    if (ctx->evkm) cudaEventDestroy(ctx->evkm);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return FRX_OK;
@@ -195,9 +201,13 @@ int frx_set_reference(frx_ctx* ctx, int32_t M, const double* ref_pos, const doub
     const double* src[6] = {ref_pos, ref_theta, ref_curv, ref_curv_d, ref_x, ref_y};
     for (int k = 0; k < 6; ++k) memcpy(h.data() + (size_t)k * Mpad, src[k], sizeof(double) * M);
     CK(ctx->ref.reserve(h.size()));
+    // on the context's stream, then synchronised: ordered against earlier plans AND complete before the (pageable)
+    // staging vector dies -- the legacy stream does not order against a non-blocking stream
+    CK(cudaMemcpyAsync(ctx->ref.p, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    CK(cudaMemcpy(ctx->ref.p, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
     ctx->M = M; ctx->Mpad = Mpad; ctx->have_ref = true;
+    ctx->origin_x = ref_x[0]; ctx->origin_y = ref_y[0];
+    ctx->compact_Nt = 0; ctx->sobb32_dirty = true;     // the fp32 cull records live in the frame of the reference path
     ctx->inv_step = (double)(M - 1) / (ref_pos[M - 1] - ref_pos[0]);
     return FRX_OK;
 }
@@ -231,10 +241,10 @@ int frx_set_time_tables(frx_ctx* ctx, int32_t nT, const double* T_values, const 
         for (int p = 0; p < 5; ++p)
             memcpy(h.data() + ((size_t)k * 5 + p) * tpitch, tpow + ((size_t)k * 5 + p) * Nt, sizeof(double) * Nt);
     CK(ctx->Ttab.reserve(nT)); CK(ctx->Tlen.reserve(nT)); CK(ctx->tpow.reserve(h.size()));
+    CK(cudaMemcpyAsync(ctx->Ttab.p, T_values, sizeof(double) * nT, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->Tlen.p, traj_len, sizeof(int) * nT, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->tpow.p, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    CK(cudaMemcpy(ctx->Ttab.p, T_values, sizeof(double) * nT, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(ctx->Tlen.p, traj_len, sizeof(int) * nT, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(ctx->tpow.p, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
     ctx->nT = nT; ctx->tpitch = tpitch; ctx->have_tables = true;
     return FRX_OK;
 }
@@ -270,8 +280,8 @@ int frx_set_obstacle_positions(frx_ctx* ctx, int32_t n, const double* pos_xy) {
     REQUIRE(pos_xy != nullptr, "frx_set_obstacle_positions: null");
     CK(cudaSetDevice(ctx->device));
     CK(ctx->obs_pos.reserve((size_t)n * 2));
+    CK(cudaMemcpyAsync(ctx->obs_pos.p, pos_xy, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    CK(cudaMemcpy(ctx->obs_pos.p, pos_xy, sizeof(double) * 2 * n, cudaMemcpyHostToDevice));
     ctx->n_obs_pos = n;
     return FRX_OK;
 }
@@ -286,7 +296,7 @@ int frx_set_static_obbs(frx_ctx* ctx, int32_t B, const double* obb) {
     frx_launch_static_prep(B, ctx->raw_sobb.p, ctx->sobb.p, ctx->stream);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(ctx->stream));
-    ctx->B = B;
+    ctx->B = B; ctx->sobb32_dirty = true;
     return FRX_OK;
 }
 
@@ -324,12 +334,19 @@ static int prepare_plan(frx_ctx* ctx, long long N, const double* d_sampling, boo
     }
     if (ctx->O > 0 && ctx->compact_Nt != Nt) {        // per-step compact records (depend on the horizon through min(Nt, len))
         const int Tp = ctx->Tp;
-        CK(ctx->opred.reserve((size_t)Tp * ctx->O * 8)); CK(ctx->ohull.reserve((size_t)Tp * ctx->O * 8));
+        CK(ctx->opred.reserve((size_t)Tp * ctx->O * 6)); CK(ctx->ohull.reserve((size_t)Tp * ctx->O * 8));
+        CK(ctx->ohull32.reserve((size_t)Tp * ctx->O));
         CK(ctx->on_pred.reserve(Tp)); CK(ctx->on_hull.reserve(Tp));
-        frx_launch_obstacle_compact(ctx->O, Tp, Nt, ctx->obs.p, ctx->obs_len.p, ctx->opred.p, ctx->ohull.p, ctx->on_pred.p,
-                                    ctx->on_hull.p, st);
+        frx_launch_obstacle_compact(ctx->O, Tp, Nt, ctx->obs.p, ctx->obs_len.p, ctx->origin_x, ctx->origin_y, ctx->opred.p,
+                                    ctx->ohull.p, ctx->ohull32.p, ctx->on_pred.p, ctx->on_hull.p, st);
         CK(cudaGetLastError());
         ctx->compact_Nt = Nt;
+    }
+    if (ctx->B > 0 && ctx->sobb32_dirty) {
+        CK(ctx->sobb32.reserve((size_t)ctx->B));
+        frx_launch_static_cull(ctx->B, ctx->sobb.p, ctx->origin_x, ctx->origin_y, ctx->sobb32.p, st);
+        CK(cudaGetLastError());
+        ctx->sobb32_dirty = false;
     }
     const int seg = (seg_hint > 0) ? seg_hint : frx_pick_seg(N, ctx->sm_count);
     const long long n_tiles = (N + 32 / seg - 1) / (32 / seg);     // one warp per tile of 32 / seg rows
@@ -355,6 +372,7 @@ static int prepare_plan(frx_ctx* ctx, long long N, const double* d_sampling, boo
     a.Ttab = ctx->Ttab.p; a.Tlen = ctx->Tlen.p; a.tpow = ctx->tpow.p; a.nT = ctx->nT; a.tpitch = ctx->tpitch;
     a.obs = ctx->obs.p; a.obs_len = ctx->obs_len.p; a.O = ctx->O; a.Tp = ctx->Tp;
     a.opred = ctx->opred.p; a.ohull = ctx->ohull.p; a.on_pred = ctx->on_pred.p; a.on_hull = ctx->on_hull.p;
+    a.ohull32 = ctx->ohull32.p; a.sobb32 = ctx->sobb32.p; a.origin_x = ctx->origin_x; a.origin_y = ctx->origin_y;
     a.obs_pos = ctx->obs_pos.p; a.n_obs_pos = ctx->n_obs_pos; a.sobb = ctx->sobb.p; a.B = ctx->B;
     a.sampling = grid_mode ? nullptr : d_sampling;
     a.g_t1 = d_t1; a.g_v1 = d_v1; a.g_d1 = d_d1; a.g_nv = g_nv; a.g_nd = g_nd;
@@ -452,7 +470,11 @@ static int enqueue_plan(frx_ctx* ctx, long long N, const double* d_sampling, boo
     ctx->last_launches = 1 + (a.defer_obs ? 1 : 0);
     CK(cudaEventRecord(ctx->evk0, st));
     CK(frx_launch_eval(a, nchunk, grid, st));
-    if (a.defer_obs) CK(frx_launch_obstacle_pass(a, ctx->sm_count, st));
+    ctx->split_last = a.defer_obs != 0;
+    if (a.defer_obs) {
+        CK(cudaEventRecord(ctx->evkm, st));
+        CK(frx_launch_obstacle_pass(a, ctx->sm_count, st));
+    }
     CK(cudaEventRecord(ctx->evk1, st));
 #ifdef FRX_TRACE
     {
@@ -482,6 +504,8 @@ static int wait_plan(frx_ctx* ctx, frx_result* out) {
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, ctx->evk0, ctx->evk1)); out->eval_kernel_ms = ms;
     CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1)); out->total_device_ms = ms;
+    out->obstacle_kernel_ms = 0.f;
+    if (ctx->split_last) { CK(cudaEventElapsedTime(&ms, ctx->evkm, ctx->evk1)); out->obstacle_kernel_ms = ms; }
     return FRX_OK;
 }
 
@@ -609,6 +633,7 @@ int frx_plan_batched(int32_t n_agents, frx_ctx** ctxs, const int64_t* n_rows, co
     CK(cudaMemcpyAsync(ctx->batch_cta.p, cta_begin.data(), sizeof(int) * (n_agents + 1), cudaMemcpyHostToDevice, st));
     CK(cudaEventRecord(ctx->evk0, st));
     CK(frx_launch_eval_batched(args.data(), ctx->batch_args.p, ctx->batch_cta.p, n_agents, max_Mpad, nchunk0, cta_begin[n_agents], st));
+    for (int a = 0; a < n_agents; ++a) ctxs[a]->split_last = false;
     // (the batch keeps the fused obstacle pass: one obstacle kernel per agent, each far below a full wave, measured
     // twice as slow -- 1.31 ms against 0.66 ms for 6 x 50,000 rows)
     CK(cudaEventRecord(ctx->evk1, st));
@@ -750,6 +775,16 @@ int frx_selftest_divc(frx_ctx* ctx, int64_t n, const double* a, double b, double
     CK(cudaMemcpyAsync(q_ieee, buf.p + 2 * n, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     buf.release();
+    return FRX_OK;
+}
+
+int frx_selftest_fp64_peak(frx_ctx* ctx, double* tflops) {
+    if (!ctx) return FRX_ERR_INVALID;
+    REQUIRE(tflops != nullptr, "frx_selftest_fp64_peak: null");
+    CK(cudaSetDevice(ctx->device));
+    cudaError_t e = cudaSuccess;
+    *tflops = frx_measure_fp64_peak(ctx->sm_count, ctx->stream, &e);
+    CK(e);
     return FRX_OK;
 }
 

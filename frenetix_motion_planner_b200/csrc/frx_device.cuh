@@ -12,7 +12,7 @@
 #endif
 #define FRX_MAX_T_VALUES 128
 #ifndef FRX_OBS_MIN_CTAS
-#define FRX_OBS_MIN_CTAS 3   // resident 256-thread blocks per SM the obstacle kernel is compiled for (register cap 85)
+#define FRX_OBS_MIN_CTAS 2   // resident 256-thread blocks per SM the obstacle kernel is compiled for (register cap 128)
 #endif
 #define FRX_EPS 1e-5
 
@@ -74,15 +74,19 @@ struct FrxKernelArgs {
     // ---- predictions / obstacles
     const double* obs;      // [O][FRX_OBS_NARR][Tp]
     const int* obs_len;     // [O] valid steps
-    const double* opred;    // [Tp][O][8] per-step compact prediction records (frx_obstacle_compact_kernel)
+    const double* opred;    // [Tp][O][6] per-step compact prediction records (frx_obstacle_compact_kernel): px, py, iv00,
+                            //            iv01 + iv10, iv11, 0 -- the quadratic form of the inverse covariance
     const double* ohull;    // [Tp][O][8] per-step compact hull records
+    const float4* ohull32;  // [Tp][O]    fp32 copies (cx - origin, cy - origin, inflated radius, 0) for the warp-level cull
     const int* on_pred;     // [Tp] records per step
     const int* on_hull;     // [Tp]
     int O, Tp;
     const double* obs_pos;  // [n_obs_pos][2] current obstacle positions (distance_to_obstacles)
     int n_obs_pos;
     const double* sobb;     // [B][8]: cx, cy, ux, uy, ha, hb, r, pad
+    const float4* sobb32;   // [B] fp32 copies (cx - origin, cy - origin, inflated radius, 0) for the warp-level cull
     int B;
+    double origin_x, origin_y;   // frame of the fp32 cull records (first reference-path vertex)
     // ---- candidates
     const double* sampling; // [N][13] or nullptr (grid mode)
     const double* g_t1; const double* g_v1; const double* g_d1;

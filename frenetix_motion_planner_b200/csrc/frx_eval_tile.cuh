@@ -550,38 +550,12 @@ __device__ __forceinline__ FrxLaneOut frx_candidate(const FrxKernelArgs& A, cons
                     if (need_col) th_n = __ldcg(q + sstride + 2 * fstride);
                 }
                 if (need_pred && i >= 1) {
-                    // the obstacles predicted at this step: 64-byte records, warp-uniform 16-byte loads
-                    const int n = __ldg(A.on_pred + (i - 1));
-                    const double2* __restrict__ rec = reinterpret_cast<const double2*>(A.opred + (size_t)(i - 1) * A.O * 8);
-                    // branch-free body (loads of the unrolled records issue together, the reciprocal chains overlap);
-                    // an operand outside the fast reciprocal's range (0, inf, nan, denormal: the ego ON an obstacle
-                    // mean) is only recorded -- the step is then redone with IEEE division
-                    const double saved = pred_sum;
-                    bool ok = true;
-#pragma unroll 4
-                    for (int o = 0; o < n; ++o) {
-                        const double2 pp = __ldg(rec + 4 * o), va = __ldg(rec + 4 * o + 1), vb = __ldg(rec + 4 * o + 2);   // (px,py) (iv00,iv10) (iv01,iv11)
-                        double ex = x - pp.x;
-                        double ey = y - pp.y;
-                        double t0 = ex * va.x + ey * va.y;
-                        double t1 = ex * vb.x + ey * vb.y;
-                        double m = t0 * ex + t1 * ey;
-                        double m2 = m * m;
-                        ok = ok && drcp_in_range(m2);
-                        pred_sum += drcp_unchecked(m2);
-                    }
-                    if (!ok) {
-                        pred_sum = saved;
-                        for (int o = 0; o < n; ++o) {
-                            const double2 pp = __ldg(rec + 4 * o), va = __ldg(rec + 4 * o + 1), vb = __ldg(rec + 4 * o + 2);
-                            double ex = x - pp.x;
-                            double ey = y - pp.y;
-                            double t0 = ex * va.x + ey * va.y;
-                            double t1 = ex * vb.x + ey * vb.y;
-                            double m = t0 * ex + t1 * ey;
-                            pred_sum += drcpg(m * m);
-                        }
-                    }
+                    // the obstacles predicted at this step: 48-byte records, warp-uniform 16-byte loads (frx_pred_step)
+                    const double xs[1] = {x}, ys[1] = {y};
+                    const bool nd[1] = {true};
+                    double acc[1] = {pred_sum};
+                    frx_pred_step<1>(A.opred + (size_t)(i - 1) * A.O * FRX_PRED_REC, __ldg(A.on_pred + (i - 1)), xs, ys, nd, acc);
+                    pred_sum = acc[0];
                 }
                 if (need_d2o) {
                     for (int o = 0; o < A.n_obs_pos; ++o) {

@@ -52,7 +52,7 @@
 extern "C" {
 #endif
 
-#define FRX_ABI_VERSION 1
+#define FRX_ABI_VERSION 2
 
 /* error codes */
 #define FRX_OK 0
@@ -118,8 +118,11 @@ typedef struct frx_result {
     int64_t n_boundary;        /* candidates overlapping a static box */
     int64_t collision_counter; /* colliding candidates the lazy reference loop would have visited */
     int64_t reason_counts[11]; /* _infeasible_count_kinematics (slot 0 = infeasible-or-invalid in list) */
-    float eval_kernel_ms;      /* device time of the eval kernel (CUDA events on the ctx stream) */
+    float eval_kernel_ms;      /* device time of the plan's kernels (eval kernel + obstacle kernel when the obstacle pass
+                                  runs as a kernel of its own), CUDA events on the ctx stream */
     float total_device_ms;     /* first H2D to last D2H of this call, CUDA events */
+    float obstacle_kernel_ms;  /* share of eval_kernel_ms spent in the obstacle kernel; 0 when the pass is fused */
+    float reserved_;
 } frx_result;
 
 int frx_abi_version(void);
@@ -196,6 +199,9 @@ int frx_selftest_fdiv(frx_ctx* ctx, int64_t n, const double* a, const double* b,
 /* diagnostics: the kernels' division by a plan constant b (dt, 100000, Nt; reciprocal precomputed on the host)
  * next to IEEE division (tests only) */
 int frx_selftest_divc(frx_ctx* ctx, int64_t n, const double* a, double b, double* q_divc, double* q_ieee);
+/* diagnostics: measured fp64 throughput of this GPU (dependent-free DFMA streams on every SM, 2 flop per FMA) in TFLOP/s:
+ * the roofline denominator of the fp64-bound obstacle kernel (bench.py) */
+int frx_selftest_fp64_peak(frx_ctx* ctx, double* tflops);
 /* use an externally created stream (e.g. torch's current stream); 0 restores the private stream */
 int frx_set_stream(frx_ctx* ctx, void* cuda_stream);
 int frx_synchronize(frx_ctx* ctx);

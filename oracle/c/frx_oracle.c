@@ -34,6 +34,7 @@
 #ifdef _OPENMP
 #include <omp.h>
 #endif
+static int orc_threads_used = 1;
 
 #define EPS 1e-5
 #define NF 14
@@ -529,6 +530,10 @@ int orc_plan(const orc_params* P, int64_t n, const double* sampling, int M, cons
     {
         double st[NF * MAXNT], cl[6], ct[6];
         hull_t eh[MAXNT];
+#ifdef _OPENMP
+#pragma omp single nowait
+        orc_threads_used = omp_get_num_threads();
+#endif
 #pragma omp for schedule(dynamic, 64)
         for (int64_t r = 0; r < n; r++) {
             int tl = 0; double mg = 0;
@@ -615,6 +620,9 @@ int orc_plan(const orc_params* P, int64_t n, const double* sampling, int M, cons
 /* exported for tests: the claim "np_sum is numpy's summation order" is checked bit-for-bit */
 double orc_np_sum(const double* a, int n) { return np_sum(a, n); }
 double orc_simps(const double* y, int n, double dx) { return simps(y, n, dx); }
+
+/* threads the last orc_plan actually ran on (bench.py asserts the CPU arm got every host thread) */
+int orc_last_threads(void) { return orc_threads_used; }
 
 int orc_max_threads(void) {
 #ifdef _OPENMP

@@ -10,9 +10,10 @@ import os
 import numpy as np
 
 from . import frenet_oracle as fo
-from .build import build, OUT
+from .build import build, build_native, OUT
 
 _lib = None
+_native = None
 
 
 class OrcParams(C.Structure):
@@ -28,15 +29,31 @@ class OrcResult(C.Structure):
                 ("n_candidates", C.c_int64), ("collision_counter", C.c_int64), ("reason_counts", C.c_int64 * 11)]
 
 
+def _declare(L):
+    L.orc_plan.restype = C.c_int
+    L.orc_max_threads.restype = C.c_int
+    L.orc_last_threads.restype = C.c_int
+    return L
+
+
 def lib():
     global _lib
     if _lib is None:
-        if not os.path.exists(OUT):
-            build()
-        _lib = C.CDLL(OUT)
-        _lib.orc_plan.restype = C.c_int
-        _lib.orc_max_threads.restype = C.c_int
+        build()                      # no-op when the library is newer than its source
+        _lib = _declare(C.CDLL(OUT))
     return _lib
+
+
+def native_lib():
+    """The host-tuned build (-O3 -march=native), compiled on this machine on first use; bench.py's CPU arm."""
+    global _native
+    if _native is None:
+        _native = _declare(C.CDLL(build_native()))
+    return _native
+
+
+def threads_used(library=None) -> int:
+    return int((library or lib()).orc_last_threads())
 
 
 def _p(a, t=C.c_double):
@@ -72,9 +89,10 @@ def pack_predictions(predictions):
 
 def plan(sampling, ref: fo.RefPath, prm: fo.Params, predictions=(), static_obbs=None,
          check_all_collisions=True, collision_check=True, want_states=True, want_margins=True, nthreads=0,
-         T_values=None, buffers=None):
-    """`buffers`: dict reused across calls (timing runs: keeps page faults of fresh arrays out of the loop)."""
-    L = lib()
+         T_values=None, buffers=None, library=None):
+    """`buffers`: dict reused across calls (timing runs: keeps page faults of fresh arrays out of the loop).
+    `nthreads` > 0 overrides OMP_NUM_THREADS (torchrun exports 1).  `library`: native_lib() for timing runs."""
+    L = library or lib()
     S = np.ascontiguousarray(sampling, dtype=np.float64)
     n = S.shape[0]
     Nt = prm.N + 1

@@ -92,7 +92,7 @@ def test_c_abi_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in include/frx.h but not exported by libfrx_b200.so"
     assert set(_capi.EXPORTS) == declared
-    assert lib.frx_abi_version() == 1
+    assert lib.frx_abi_version() == 2
 
 
 def test_no_cpu_fallback_without_a_gpu():
