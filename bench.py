@@ -105,13 +105,14 @@ def build_workload(name: str, world: int):
         x_cl = ([15.0, 12.0, 0.2], [0.1, 0.05, 0.0])
         t1 = np.unique(np.round(np.linspace(1.1, 5.0, 50), 2))
         v_lo, v_hi = syn.velocity_interval(12.0, syn.VEHICLE_2["a_max"], 5.0, syn.VEHICLE_2["v_max"])
-        v1 = np.linspace(v_lo, v_hi, 448)
+        nv5 = int(os.environ.get("FRX_BENCH_C5_V", "448"))      # tuning aid (profiler captures): fewer rows, not the headline
+        v1 = np.linspace(v_lo, v_hi, nv5)
         d1 = np.linspace(-3.0, 3.0, 447)
         preds = syn.synthetic_predictions(poly, 50, 51, 0.1, seed=2025, s_hi=200.0)
         total = t1.size * v1.size * d1.size
         return dict(name=name, polyline=poly, x_cl=x_cl, t1=t1, v1=v1, d1=d1, N=50, dt=0.1, x0_orientation=0.1, v_des=13.0,
                     v0=12.0, preds=preds, scaling="strong", grid_mode=True,
-                    label=f"configs[4]: R=200 m arc, {t1.size}t x 448v x 447d = {total:,} candidates sharded over the "
+                    label=f"configs[4]: R=200 m arc, {t1.size}t x {nv5}v x 447d = {total:,} candidates sharded over the "
                           f"GPUs, 51 samples, 5 cost terms, 50 predicted obstacles, rows generated on device, fp64")
     if name == "config4":
         # multi-agent: 6 agents (the ego + the 5 cars of the T-junction fixture are agents in main_multiagent.py),

@@ -14,11 +14,12 @@
 #include "frx_device.cuh"
 
 // launchers implemented in frx_kernels.cu
-size_t frx_eval_smem_bytes(int Mpad, int nchunk, bool obs);
-cudaError_t frx_launch_eval(const FrxKernelArgs& a, int nchunk, int grid, cudaStream_t st);
-cudaError_t frx_eval_occupancy(int Mpad, int nchunk, int* blocks_per_sm);
+size_t frx_eval_smem_bytes(int Mpad, int Nt);
+int frx_memo_pitch_host(int Nt);
+cudaError_t frx_launch_eval(const FrxKernelArgs& a, int Nt, int grid, cudaStream_t st);
+cudaError_t frx_eval_occupancy(int Mpad, int Nt, int* blocks_per_sm);
 cudaError_t frx_launch_eval_batched(const FrxKernelArgs* h_agents, const FrxKernelArgs* d_agents, const int* d_cta_begin,
-                                    int n_agents, int max_Mpad, int nchunk, int grid, cudaStream_t st);
+                                    int n_agents, int max_Mpad, int Nt, int grid, cudaStream_t st);
 void frx_launch_obstacle_prep(int O, int T, int Tp, const double* pos, const double* cov, const double* theta,
                               const double* hl, const double* hw, double* obs, cudaStream_t st);
 void frx_launch_static_prep(int B, const double* obb, double* out, cudaStream_t st);
@@ -32,7 +33,8 @@ void frx_launch_gather(const double* states, long long Np, int Nt, int Ntp, cons
                        long long n_idx, uint32_t mask, double* out, cudaStream_t st);
 void frx_features(const FrxKernelArgs& a, bool* obs, bool* xcost);
 int frx_pick_seg(long long n_rows, int sm_count);
-cudaError_t frx_launch_obstacle_pass(const FrxKernelArgs& a, int sm_count, cudaStream_t st);
+cudaError_t frx_launch_obstacle_pass(FrxKernelArgs& a, int sm_count, cudaStream_t st, int* launches);
+size_t frx_obstacle_scratch_elems(long long N);
 int frx_obstacle_pass_max_grid(int sm_count);
 
 void frx_launch_selftest_fdiv(long long n, const double* a, const double* b, double* q1, double* q2, cudaStream_t st);
@@ -83,6 +85,7 @@ struct frx_ctx {
     DevBuf<double> sampling, grid;
     DevBuf<double> states, costs, total; DevBuf<uint32_t> flags; DevBuf<int> traj_len;
     DevBuf<unsigned long long> blockcnt;
+    DevBuf<double> obs_part; DevBuf<uint32_t> obs_hit;     // scratch of the step-chunked obstacle pass
     DevBuf<FrxBest> blockbest, winner; DevBuf<unsigned long long> counters;
     DevBuf<long long> gidx; DevBuf<double> gout;
     DevBuf<FrxKernelArgs> batch_args; DevBuf<int> batch_cta;
@@ -94,7 +97,7 @@ struct frx_ctx {
     long long lastN = 0, lastNp = 0; int lastK = 0, lastNt = 0, lastNtp = 0;
     bool last_all_fields = false;     // the last plan materialised all 14 state planes
     int last_launches = 0;            // kernels the last plan launched (eval, obstacle, collision counter, set-up)
-    int occ_Mpad = -1, occ_nchunk = -1, occ_blocks = 1;
+    int occ_Mpad = -1, occ_Nt = -1, occ_blocks = 1;
 };
 
 #define CK(call)                                                                       \
@@ -162,7 +165,7 @@ int frx_destroy(frx_ctx* ctx) {
     ctx->raw_hl.release(); ctx->raw_hw.release(); ctx->obs_len.release(); ctx->obs_pos.release();
     ctx->sobb.release(); ctx->raw_sobb.release(); ctx->sampling.release(); ctx->grid.release();
     ctx->states.release(); ctx->costs.release(); ctx->total.release(); ctx->flags.release(); ctx->traj_len.release();
-    ctx->blockcnt.release(); ctx->blockbest.release(); ctx->winner.release(); ctx->counters.release(); ctx->gidx.release(); ctx->gout.release(); ctx->batch_args.release(); ctx->batch_cta.release();
+    ctx->blockcnt.release(); ctx->obs_part.release(); ctx->obs_hit.release(); ctx->blockbest.release(); ctx->winner.release(); ctx->counters.release(); ctx->gidx.release(); ctx->gout.release(); ctx->batch_args.release(); ctx->batch_cta.release();
     if (ctx->h_res) cudaFreeHost(ctx->h_res);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -195,7 +198,7 @@ int frx_set_reference(frx_ctx* ctx, int32_t M, const double* ref_pos, const doub
     REQUIRE(M >= 2 && ref_pos && ref_theta && ref_curv && ref_curv_d && ref_x && ref_y, "frx_set_reference: bad arguments");
     CK(cudaSetDevice(ctx->device));
     int Mpad = (M + 1) & ~1;
-    REQUIRE(frx_eval_smem_bytes(Mpad, 2, true) <= (size_t)ctx->max_smem_optin,
+    REQUIRE(frx_eval_smem_bytes(Mpad, ctx->have_params ? ctx->prm.N + 1 : 64) <= (size_t)ctx->max_smem_optin,
             "frx_set_reference: reference path too long for the shared-memory table");
     std::vector<double> h((size_t)6 * Mpad, 0.0);
     const double* src[6] = {ref_pos, ref_theta, ref_curv, ref_curv_d, ref_x, ref_y};
@@ -236,10 +239,21 @@ int frx_set_time_tables(frx_ctx* ctx, int32_t nT, const double* T_values, const 
     const int tpitch = nchunk_for(Nt) * 32;
     for (int k = 0; k < nT; ++k)
         REQUIRE(traj_len[k] >= 1 && traj_len[k] <= Nt, "frx_set_time_tables: traj_len exceeds the planning horizon");
-    std::vector<double> h((size_t)nT * 5 * tpitch, 0.0);
+    // The rounded powers of step i do not depend on the duration: np.round(np.arange(0, T + dt, dt), 5) is 0 + i * dt for
+    // every T (reactive_planner.py:296-300), only the number of samples differs.  The kernels therefore keep ONE table
+    // [5][tpitch] per CTA in shared memory; a caller whose tables disagree on a common step is refused.
+    std::vector<double> h((size_t)5 * tpitch, 0.0);
+    std::vector<int> have(Nt, 0);
     for (int k = 0; k < nT; ++k)
-        for (int p = 0; p < 5; ++p)
-            memcpy(h.data() + ((size_t)k * 5 + p) * tpitch, tpow + ((size_t)k * 5 + p) * Nt, sizeof(double) * Nt);
+        for (int i = 0; i < traj_len[k]; ++i) {
+            for (int p = 0; p < 5; ++p) {
+                const double v = tpow[((size_t)k * 5 + p) * Nt + i];
+                double& m = h[(size_t)p * tpitch + i];
+                REQUIRE(!have[i] || m == v, "frx_set_time_tables: the time-power tables of two durations differ on a common step");
+                m = v;
+            }
+            have[i] = 1;
+        }
     CK(ctx->Ttab.reserve(nT)); CK(ctx->Tlen.reserve(nT)); CK(ctx->tpow.reserve(h.size()));
     CK(cudaMemcpyAsync(ctx->Ttab.p, T_values, sizeof(double) * nT, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->Tlen.p, traj_len, sizeof(int) * nT, cudaMemcpyHostToDevice, ctx->stream));
@@ -304,7 +318,7 @@ int frx_set_static_obbs(frx_ctx* ctx, int32_t B, const double* obb) {
 static int prepare_plan(frx_ctx* ctx, long long N, const double* d_sampling, bool grid_mode, int g_nv, int g_nd,
                         const double* d_t1, const double* d_v1, const double* d_d1, const double* xcl,
                         long long row_first, long long row_base, int max_grid, int seg_hint, cudaStream_t st,
-                        FrxKernelArgs* a_out, int* grid_out, int* nchunk_out) {
+                        FrxKernelArgs* a_out, int* grid_out, int* Nt_out) {
     REQUIRE(ctx->have_params && ctx->have_ref && ctx->have_tables,
             "frx_plan: frx_set_params, frx_set_reference and frx_set_time_tables must be called first");
     const frx_params& p = ctx->prm;
@@ -316,11 +330,13 @@ static int prepare_plan(frx_ctx* ctx, long long N, const double* d_sampling, boo
     else if (need_xyt) CK(ctx->states.reserve((size_t)3 * Nt * Np));
     CK(ctx->costs.reserve((size_t)N * (K > 0 ? K : 1))); CK(ctx->total.reserve(N)); CK(ctx->flags.reserve(N));
     CK(ctx->traj_len.reserve(N));
-    if (ctx->occ_Mpad != ctx->Mpad || ctx->occ_nchunk != nchunk) {
+    if (ctx->occ_Mpad != ctx->Mpad || ctx->occ_Nt != Nt) {
         int b = 1;
-        CK(frx_eval_occupancy(ctx->Mpad, nchunk, &b));
+        REQUIRE(frx_eval_smem_bytes(ctx->Mpad, Nt) <= (size_t)ctx->max_smem_optin,
+                "frx_plan: reference path too long for the shared-memory table at this planning horizon");
+        CK(frx_eval_occupancy(ctx->Mpad, Nt, &b));
         REQUIRE(b >= 1, "frx_plan: eval kernel does not fit on an SM with this reference length");
-        ctx->occ_blocks = b; ctx->occ_Mpad = ctx->Mpad; ctx->occ_nchunk = nchunk;
+        ctx->occ_blocks = b; ctx->occ_Mpad = ctx->Mpad; ctx->occ_Nt = Nt;
     }
     if (ctx->O > 0 && ctx->Tp != nchunk * 32) {      // (re)build the obstacle table for this horizon
         const int Tp = nchunk * 32;
@@ -370,6 +386,7 @@ static int prepare_plan(frx_ctx* ctx, long long N, const double* d_sampling, boo
     a.store_states = p.store_states; a.check_collisions = p.check_collisions;
     a.ref = ctx->ref.p; a.M = ctx->M; a.Mpad = ctx->Mpad;
     a.Ttab = ctx->Ttab.p; a.Tlen = ctx->Tlen.p; a.tpow = ctx->tpow.p; a.nT = ctx->nT; a.tpitch = ctx->tpitch;
+    a.mpitch = frx_memo_pitch_host(Nt);
     a.obs = ctx->obs.p; a.obs_len = ctx->obs_len.p; a.O = ctx->O; a.Tp = ctx->Tp;
     a.opred = ctx->opred.p; a.ohull = ctx->ohull.p; a.on_pred = ctx->on_pred.p; a.on_hull = ctx->on_hull.p;
     a.ohull32 = ctx->ohull32.p; a.sobb32 = ctx->sobb32.p; a.origin_x = ctx->origin_x; a.origin_y = ctx->origin_y;
@@ -386,7 +403,7 @@ static int prepare_plan(frx_ctx* ctx, long long N, const double* d_sampling, boo
         CK(cudaMemsetAsync(ctx->counters.p, 0, sizeof(unsigned long long) * FRX_NUM_COUNTERS, st));
         ctx->counters_dirty = false;
     }
-    *a_out = a; *grid_out = grid; *nchunk_out = nchunk;
+    *a_out = a; *grid_out = grid; *Nt_out = Nt;
     ctx->lastN = N; ctx->lastNp = Np; ctx->lastK = K; ctx->lastNt = Nt; ctx->lastNtp = Ntp;
     ctx->last_all_fields = p.store_states != 0;
     return FRX_OK;
@@ -443,8 +460,12 @@ static int choose_obstacle_split(frx_ctx* ctx, FrxKernelArgs* a, int grid) {
     if (split) {
         const size_t need = (size_t)frx_obstacle_pass_max_grid(ctx->sm_count);
         CK(ctx->blockbest.reserve(need > (size_t)grid ? need : (size_t)grid));
+        if (a->N <= (1LL << 22)) {      // plans this small may be cut into step chunks (frx_obstacle_chunks)
+            CK(ctx->obs_part.reserve(frx_obstacle_scratch_elems(a->N)));
+            CK(ctx->obs_hit.reserve(frx_obstacle_scratch_elems(a->N)));
+        }
     }
-    a->blockbest = ctx->blockbest.p;
+    a->blockbest = ctx->blockbest.p; a->obs_part = ctx->obs_part.p; a->obs_hit = ctx->obs_hit.p; a->obs_chunks = 1;
     return FRX_OK;
 }
 
@@ -453,9 +474,9 @@ static int enqueue_plan(frx_ctx* ctx, long long N, const double* d_sampling, boo
                         long long row_first, long long row_base) {
     cudaStream_t st = ctx->stream;
     FrxKernelArgs a;
-    int grid = 1, nchunk = 1;
+    int grid = 1, Nt = 1;
     int rc = prepare_plan(ctx, N, d_sampling, grid_mode, g_nv, g_nd, d_t1, d_v1, d_d1, xcl, row_first, row_base, 0, 0, st,
-                          &a, &grid, &nchunk);
+                          &a, &grid, &Nt);
     if (rc != FRX_OK) return rc;
     ctx->counters_dirty = true;          // cleared again once the launch sequence has completed
 #ifdef FRX_TRACE
@@ -467,13 +488,15 @@ static int enqueue_plan(frx_ctx* ctx, long long N, const double* d_sampling, boo
 #endif
     rc = choose_obstacle_split(ctx, &a, grid);
     if (rc != FRX_OK) return rc;
-    ctx->last_launches = 1 + (a.defer_obs ? 1 : 0);
+    ctx->last_launches = 1;
     CK(cudaEventRecord(ctx->evk0, st));
-    CK(frx_launch_eval(a, nchunk, grid, st));
+    CK(frx_launch_eval(a, Nt, grid, st));
     ctx->split_last = a.defer_obs != 0;
     if (a.defer_obs) {
         CK(cudaEventRecord(ctx->evkm, st));
-        CK(frx_launch_obstacle_pass(a, ctx->sm_count, st));
+        int n_obs_launches = 0;
+        CK(frx_launch_obstacle_pass(a, ctx->sm_count, st, &n_obs_launches));
+        ctx->last_launches += n_obs_launches;
     }
     CK(cudaEventRecord(ctx->evk1, st));
 #ifdef FRX_TRACE
@@ -606,9 +629,9 @@ int frx_plan_batched(int32_t n_agents, frx_ctx** ctxs, const int64_t* n_rows, co
     }
     // CTA budget: the persistent grid of one launch, split over the agents in proportion to their rows
     {
-        int nchunk = nchunk_for(ctx->prm.N + 1), b = 1;
+        int b = 1;
         for (int a = 0; a < n_agents; ++a) if (ctxs[a]->Mpad > max_Mpad) max_Mpad = ctxs[a]->Mpad;
-        CK(frx_eval_occupancy(max_Mpad, nchunk, &b));
+        CK(frx_eval_occupancy(max_Mpad, ctx->prm.N + 1, &b));
         REQUIRE(b >= 1, "frx_plan_batched: eval kernel does not fit on an SM");
         occ = b;
     }

@@ -69,8 +69,9 @@ struct FrxKernelArgs {
     // ---- time tables
     const double* Ttab;     // [nT] distinct durations
     const int* Tlen;        // [nT] traj_len
-    const double* tpow;     // [nT][5][tpitch]
+    const double* tpow;     // [5][tpitch] rounded powers t, t^2 .. t^5 of the step times (the same for every duration)
     int nT, tpitch;
+    int mpitch;             // step pitch of the per-warp memo rows in shared memory (Nt rounded up to 4)
     // ---- predictions / obstacles
     const double* obs;      // [O][FRX_OBS_NARR][Tp]
     const int* obs_len;     // [O] valid steps
@@ -103,6 +104,9 @@ struct FrxKernelArgs {
     int defer_obs;          // 1: the eval kernel skips the obstacle pass, arg-min and result record; frx_obstacle_kernel
                             //    (launched right behind it) does them
     int keep_xyt;           // store_states == 0 but the obstacle pass needs the x, y, theta planes
+    int obs_chunks;         // step chunks of the split obstacle pass (1: frx_obstacle_kernel finishes the plan inline)
+    double* obs_part;       // [obs_chunks][N] partial prediction cost of a chunk
+    uint32_t* obs_hit;      // [obs_chunks][N] first colliding hull of a chunk: collide | boundary << 8, 127 = none
     double* costs;          // [N][n_costs]
     double* total;          // [N]
     uint32_t* flags;        // [N]

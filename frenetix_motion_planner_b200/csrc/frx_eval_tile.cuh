@@ -47,7 +47,10 @@ __device__ __forceinline__ unsigned long long frx_now() {
 #define FRX_TRW nullptr
 #endif
 
-enum { M_S = 0, M_SD, M_SDD, M_INTERP, M_KR, M_KRD, M_PX, M_PY, M_SN, M_CS, M_T1, M_T2, M_T3, M_T4, M_T5, M_FIELDS };
+enum { M_S = 0, M_SD, M_SDD, M_INTERP, M_KR, M_KRD, M_PX, M_PY, M_SN, M_CS, M_FIELDS };
+// rows of the time-power table t, t^2 .. t^5 (shared by the CTA: the rounded powers of step i do not depend on the duration,
+// np.arange(0, T + dt, dt) is 0 + i * dt for every T -- only the number of samples does; frx_set_time_tables checks it)
+enum { T_1 = 0, T_2, T_3, T_4, T_5, T_ROWS };
 
 struct FrxMemoHdr {        // one per memo slot (shared memory)
     double key[5];         // t1, s0, ss0, sss0, ss1 the slot was filled for
@@ -57,8 +60,9 @@ struct FrxMemoHdr {        // one per memo slot (shared memory)
 
 #define FRX_MEMO_SLOTS 2
 
-__host__ __device__ inline size_t frx_tile_smem_bytes(int Mpad, int tpitch) {
-    return (size_t)(6 * Mpad + FRX_MAX_T_VALUES + FRX_WARPS_PER_CTA * FRX_MEMO_SLOTS * M_FIELDS * tpitch) * sizeof(double) +
+__host__ __device__ inline int frx_memo_pitch(int Nt) { return (Nt + 3) & ~3; }
+__host__ __device__ inline size_t frx_tile_smem_bytes(int Mpad, int tpitch, int mpitch) {
+    return (size_t)(6 * Mpad + FRX_MAX_T_VALUES + T_ROWS * tpitch + FRX_WARPS_PER_CTA * FRX_MEMO_SLOTS * M_FIELDS * mpitch) * sizeof(double) +
            FRX_WARPS_PER_CTA * FRX_MEMO_SLOTS * sizeof(FrxMemoHdr) + 16 + FRX_WARPS_PER_CTA * sizeof(FrxBest) +
            (size_t)FRX_WARPS_PER_CTA * 32 * 13 * sizeof(double);
 }
@@ -88,11 +92,11 @@ struct FrxSimpson {
 // :457-460, :536-547; polynomial_trajectory.py:452-488 (quartic, closed form)
 // ------------------------------------------------------------------------------------------------------------
 __device__ __noinline__ void frx_memo_fill(const FrxKernelArgs& A, const double* __restrict__ s_ref, const double* __restrict__ s_Ttab,
-                                           const int* __restrict__ s_Tlen, unsigned long long* trw,
+                                           const int* __restrict__ s_Tlen, const double* __restrict__ s_tp, unsigned long long* trw,
                                            double* __restrict__ mt, FrxMemoHdr* __restrict__ hdr, const double T, const double s0,
                                            const double ss0, const double sss0, const double ss1) {
     const int lane = threadIdx.x & 31;
-    const int Mpad = A.Mpad, M = A.M, Nt = A.Nt, TP = A.tpitch;
+    const int Mpad = A.Mpad, M = A.M, Nt = A.Nt, TP = A.tpitch, MP = A.mpitch;
     const double* __restrict__ rp = s_ref;
     const double* __restrict__ rth = s_ref + Mpad;
     const double* __restrict__ rc = s_ref + 2 * Mpad;
@@ -126,7 +130,6 @@ __device__ __noinline__ void frx_memo_fill(const FrxKernelArgs& A, const double*
     }
     const int traj_len = s_Tlen[tix];      // (shared memory: a global load here would put a second round trip in front of
                                            // the loads at index traj_len - 1 below)
-    const double* __restrict__ tp = A.tpow + (size_t)tix * 5 * TP;
     Poly L;
     {
         double T2 = T * T, T3 = T2 * T;
@@ -138,20 +141,11 @@ __device__ __noinline__ void frx_memo_fill(const FrxKernelArgs& A, const double*
         L.c5 = 0.0;
     }
     const int il = traj_len - 1;
-    // the time-power rows of this duration go into the memo first (the lateral pass re-reads them): ONE round of global
-    // loads for the whole fill -- the entries at step 0 and step traj_len - 1 needed next are then read from shared memory
-    for (int c0 = 0; c0 < TP; c0 += 32) {
-        const int i = c0 + lane;
-        const double t = __ldg(tp + i), t2 = __ldg(tp + TP + i), t3 = __ldg(tp + 2 * TP + i), t4 = __ldg(tp + 3 * TP + i),
-                     t5 = __ldg(tp + 4 * TP + i);
-        mt[M_T1 * TP + i] = t; mt[M_T2 * TP + i] = t2; mt[M_T3 * TP + i] = t3; mt[M_T4 * TP + i] = t4; mt[M_T5 * TP + i] = t5;
-    }
-    __syncwarp();
     double s_last = 0.0, sd_last = 0.0, s_inc = 0.0;
-    const double s_first = poly_pos(L, mt[M_T1 * TP], mt[M_T2 * TP], mt[M_T3 * TP], mt[M_T4 * TP], mt[M_T5 * TP]);
+    const double s_first = poly_pos(L, s_tp[T_1 * TP], s_tp[T_2 * TP], s_tp[T_3 * TP], s_tp[T_4 * TP], s_tp[T_5 * TP]);
     if (traj_len < Nt) {   // values of the last polynomial sample feed the extension of every later step
-        double tl = mt[M_T1 * TP + il], tl2 = mt[M_T2 * TP + il], tl3 = mt[M_T3 * TP + il], tl4 = mt[M_T4 * TP + il],
-               tl5 = mt[M_T5 * TP + il];
+        double tl = s_tp[T_1 * TP + il], tl2 = s_tp[T_2 * TP + il], tl3 = s_tp[T_3 * TP + il], tl4 = s_tp[T_4 * TP + il],
+               tl5 = s_tp[T_5 * TP + il];
         s_last = poly_pos(L, tl, tl2, tl3, tl4, tl5);
         sd_last = poly_vel(L, tl, tl2, tl3, tl4);
         s_inc = dT * sd_last;
@@ -164,8 +158,8 @@ __device__ __noinline__ void frx_memo_fill(const FrxKernelArgs& A, const double*
         const bool act = i < Nt;
         double vs = 0, vsd = 0, vsdd = 0;
         {
-            const double t = mt[M_T1 * TP + i], t2 = mt[M_T2 * TP + i], t3 = mt[M_T3 * TP + i], t4 = mt[M_T4 * TP + i],
-                         t5 = mt[M_T5 * TP + i];
+            const double t = s_tp[T_1 * TP + i], t2 = s_tp[T_2 * TP + i], t3 = s_tp[T_3 * TP + i], t4 = s_tp[T_4 * TP + i],
+                         t5 = s_tp[T_5 * TP + i];
             if (i < traj_len) {
                 vs = poly_pos(L, t, t2, t3, t4, t5);
                 vsd = poly_vel(L, t, t2, t3, t4);
@@ -202,11 +196,13 @@ __device__ __noinline__ void frx_memo_fill(const FrxKernelArgs& A, const double*
         double sn, cs;
         sincos(thr, &sn, &cs);
         FRX_MSTAMP(13);  // sincos
-        mt[M_S * TP + i] = vs; mt[M_SD * TP + i] = vsd; mt[M_SDD * TP + i] = vsdd;
-        mt[M_INTERP * TP + i] = interp;
-        mt[M_KR * TP + i] = k_r; mt[M_KRD * TP + i] = k_r_d;
-        mt[M_PX * TP + i] = px; mt[M_PY * TP + i] = py;
-        mt[M_SN * TP + i] = sn; mt[M_CS * TP + i] = cs;
+        if (i < MP) {
+            mt[M_S * MP + i] = vs; mt[M_SD * MP + i] = vsd; mt[M_SDD * MP + i] = vsdd;
+            mt[M_INTERP * MP + i] = interp;
+            mt[M_KR * MP + i] = k_r; mt[M_KRD * MP + i] = k_r_d;
+            mt[M_PX * MP + i] = px; mt[M_PY * MP + i] = py;
+            mt[M_SN * MP + i] = sn; mt[M_CS * MP + i] = cs;
+        }
     }
     if (lane == 0) {
         hdr->traj_len = traj_len;
@@ -238,13 +234,14 @@ template <int SEG, bool OBS, bool XCOST>
 __device__ __forceinline__ FrxLaneOut frx_candidate(const FrxKernelArgs& A, const unsigned cost_mask, const unsigned pass,
                                                     const long long r, const double T, const double d0, const double dd0,
                                                     const double ddd0, const double d1, const double dd1, const double ddd1,
-                                                    const double* __restrict__ mt, const FrxMemoHdr* __restrict__ H) {
+                                                    const double* __restrict__ mt, const FrxMemoHdr* __restrict__ H,
+                                                    const double* __restrict__ s_tp) {
     constexpr int C = 32 / SEG;                 // candidates per tile
     const int lane = threadIdx.x & 31;
     const int cand = lane & (C - 1), seg = lane / C;
     FrxLaneOut out;
     out.ev = 0; out.total = 0.0; out.winner_ok = false; out.t_missing = false;
-    const int Nt = A.Nt, TP = A.tpitch;
+    const int Nt = A.Nt, TP = A.tpitch, MP = A.mpitch;
     const double dT = A.dt;
     const bool low = A.low != 0, draw = A.draw != 0, debug = A.debug != 0;
     const bool brk = !draw && !debug;
@@ -276,9 +273,9 @@ __device__ __forceinline__ FrxLaneOut frx_candidate(const FrxKernelArgs& A, cons
     double d_last = 0.0;
     if (traj_len < Nt && !dead) {
         if (!low) {
-            d_last = poly_pos(Q, mt[M_T1 * TP + il], mt[M_T2 * TP + il], mt[M_T3 * TP + il], mt[M_T4 * TP + il], mt[M_T5 * TP + il]);
+            d_last = poly_pos(Q, s_tp[T_1 * TP + il], s_tp[T_2 * TP + il], s_tp[T_3 * TP + il], s_tp[T_4 * TP + il], s_tp[T_5 * TP + il]);
         } else {
-            double q1 = mt[M_S * TP + il] - s_first, q2 = q1 * q1, q3 = q2 * q1, q4 = q2 * q2, q5 = q4 * q1;
+            double q1 = mt[M_S * MP + il] - s_first, q2 = q1 * q1, q3 = q2 * q1, q4 = q2 * q2, q5 = q4 * q1;
             d_last = poly_pos(Q, q1, q2, q3, q4, q5);
         }
     }
@@ -309,14 +306,14 @@ __device__ __forceinline__ FrxLaneOut frx_candidate(const FrxKernelArgs& A, cons
     // first step of a later segment: gates that need step i0 - 1 are completed after the loop
     uint32_t g_first = 0;
     double th_first = 0.0, ka_first = 0.0, vi_first = 0.0, a_first = 0.0, thc_first = 0.0;
-    if (SEG > 1 && seg > 0 && evaluate && !low && i0 < i1 && !(mt[M_SD * TP + i0] > 0.001)) {
+    if (SEG > 1 && seg > 0 && evaluate && !low && i0 < i1 && !(mt[M_SD * MP + i0] > 0.001)) {
         // the segment starts in stand-still: theta_gl of the last moving step before it (:423-454), or x_0's
         for (int j = i0 - 1; j >= 0; --j) {
-            const double sdj = mt[M_SD * TP + j];
+            const double sdj = mt[M_SD * MP + j];
             if (sdj > 0.001) {
                 double ddj = 0.0;
-                if (j < traj_len) ddj = poly_vel(Q, mt[M_T1 * TP + j], mt[M_T2 * TP + j], mt[M_T3 * TP + j], mt[M_T4 * TP + j]);
-                th_prev = datan(ddivf(ddj, sdj)) + mt[M_INTERP * TP + j];
+                if (j < traj_len) ddj = poly_vel(Q, s_tp[T_1 * TP + j], s_tp[T_2 * TP + j], s_tp[T_3 * TP + j], s_tp[T_4 * TP + j]);
+                th_prev = datan(ddivf(ddj, sdj)) + mt[M_INTERP * MP + j];
                 break;
             }
         }
@@ -345,14 +342,14 @@ __device__ __forceinline__ FrxLaneOut frx_candidate(const FrxKernelArgs& A, cons
         // independent fp64 chains (the two slope divisions, the reciprocal square root, the 1/qc refinement, the a_max(v)
         // quotient) are scheduled together; the unchecked reciprocal sequences are bit-identical to IEEE division inside
         // their range, a divisor outside it is detected and redone with IEEE division.
-        const double si = mt[M_S * TP + i], sdi = mt[M_SD * TP + i], sddi = mt[M_SDD * TP + i];
-        const double interp = mt[M_INTERP * TP + i];
-        const double k_r = mt[M_KR * TP + i], k_r_d = mt[M_KRD * TP + i];
+        const double si = mt[M_S * MP + i], sdi = mt[M_SD * MP + i], sddi = mt[M_SDD * MP + i];
+        const double interp = mt[M_INTERP * MP + i];
+        const double k_r = mt[M_KR * MP + i], k_r_d = mt[M_KRD * MP + i];
         double di, ddi, dddi;
         {
             const double q1 = si - s_first, q2 = q1 * q1, q3 = q2 * q1, q4 = q2 * q2, q5 = q4 * q1;
-            const double u1 = low ? q1 : mt[M_T1 * TP + i], u2 = low ? q2 : mt[M_T2 * TP + i], u3 = low ? q3 : mt[M_T3 * TP + i],
-                         u4 = low ? q4 : mt[M_T4 * TP + i], u5 = low ? q5 : mt[M_T5 * TP + i];
+            const double u1 = low ? q1 : s_tp[T_1 * TP + i], u2 = low ? q2 : s_tp[T_2 * TP + i], u3 = low ? q3 : s_tp[T_3 * TP + i],
+                         u4 = low ? q4 : s_tp[T_4 * TP + i], u5 = low ? q5 : s_tp[T_5 * TP + i];
             const bool inpoly = i < traj_len;
             const double pd = poly_pos(Q, u1, u2, u3, u4, u5), pv = poly_vel(Q, u1, u2, u3, u4), pa = poly_acc(Q, u1, u2, u3);
             di = inpoly ? pd : d_last; ddi = inpoly ? pv : 0.0; dddi = inpoly ? pa : 0.0;
@@ -420,8 +417,8 @@ __device__ __forceinline__ FrxLaneOut frx_candidate(const FrxKernelArgs& A, cons
         double kd = has_prev ? (kappa - ka_prev) : 0.0;   // np.append([0], np.diff(kappa_gl))
         // :536-547 Cartesian position: zero from the first out-of-domain step on
         const bool inside = i < first_none;
-        double xi = inside ? (mt[M_PX * TP + i] - di * mt[M_SN * TP + i]) : 0.0;
-        double yi = inside ? (mt[M_PY * TP + i] + di * mt[M_CS * TP + i]) : 0.0;
+        double xi = inside ? (mt[M_PX * MP + i] - di * mt[M_SN * MP + i]) : 0.0;
+        double yi = inside ? (mt[M_PY * MP + i] + di * mt[M_CS * MP + i]) : 0.0;
         if (evaluate) {
             if (deferred) {
                 g_first = g; th_first = th_gl; ka_first = kappa; vi_first = vi; a_first = ai; thc_first = th_cl;
@@ -526,6 +523,7 @@ __device__ __forceinline__ FrxLaneOut frx_candidate(const FrxKernelArgs& A, cons
     // collision sweep (planner.py:329-378, collision_check.py:110-200); obstacle data is warp-uniform per step
     double pred_sum = 0.0, d2o_sum = 0.0;
     bool collide = false, boundary = false;
+    int col_k = 64, bnd_k = 64;          // ego hull index of the first hit (64 = none)
     if (SEG > 1 && (OBS || XCOST)) __syncwarp(pass);     // the x, y, theta planes of the other segments are visible now
     if (OBS || XCOST) {
         const bool need_pred = OBS && costed && (cost_mask & (1u << FRX_COST_PREDICTION)) && A.O > 0;
@@ -594,7 +592,7 @@ __device__ __forceinline__ FrxLaneOut frx_candidate(const FrxKernelArgs& A, cons
                                     near_mask &= near_mask - 1;
                                     const double2 cc = __ldg(rec + 4 * o), ru = __ldg(rec + 4 * o + 1), uh = __ldg(rec + 4 * o + 2);
                                     if (obb_overlap(e, cc.x, cc.y, ru.y, uh.x, uh.y, __ldg(reinterpret_cast<const double*>(rec + 4 * o + 3)))) {
-                                        collide = true;
+                                        collide = true; col_k = k;
                                         break;
                                     }
                                 }
@@ -607,7 +605,7 @@ __device__ __forceinline__ FrxLaneOut frx_candidate(const FrxKernelArgs& A, cons
                                 double ddx = __ldg(sb) - e.cx, ddy = __ldg(sb + 1) - e.cy;
                                 if (ddx * ddx + ddy * ddy > rr * rr) continue;
                                 if (obb_overlap(e, __ldg(sb), __ldg(sb + 1), __ldg(sb + 2), __ldg(sb + 3), __ldg(sb + 4), __ldg(sb + 5))) {
-                                    boundary = true;
+                                    boundary = true; bnd_k = k;
                                     break;
                                 }
                             }
@@ -632,6 +630,12 @@ __device__ __forceinline__ FrxLaneOut frx_candidate(const FrxKernelArgs& A, cons
             for (int sgm = 0; sgm < SEG; ++sgm) mine |= 1u << (cand + sgm * C);
             collide = (cm2 & mine) != 0;
             boundary = (bm2 & mine) != 0;
+            // every segment lane found the first hit of ITS steps: the candidate's first hit is the earliest of them
+#pragma unroll
+            for (int off = C; off < 32; off <<= 1) {
+                col_k = min(col_k, __shfl_xor_sync(pass, col_k, off));
+                bnd_k = min(bnd_k, __shfl_xor_sync(pass, bnd_k, off));
+            }
         }
     }
     if (dead) {
@@ -675,8 +679,8 @@ __device__ __forceinline__ FrxLaneOut frx_candidate(const FrxKernelArgs& A, cons
     if (in_list) fl |= FRX_FLAG_IN_LIST;
     if (costed) fl |= FRX_FLAG_COSTED;
     if (candidate) fl |= FRX_FLAG_CANDIDATE;
-    if (collide) fl |= FRX_FLAG_COLLIDE;
-    if (boundary) fl |= FRX_FLAG_BOUNDARY;
+    if (collide) fl |= FRX_FLAG_COLLIDE | ((uint32_t)(col_k & 63) << FRX_FLAG_COLLIDE_STEP_SHIFT);
+    if (boundary) fl |= FRX_FLAG_BOUNDARY | ((uint32_t)(bnd_k & 63) << FRX_FLAG_BOUNDARY_STEP_SHIFT);
     A.total[r] = total;
     A.flags[r] = fl;
     A.traj_len[r] = traj_len;
@@ -703,15 +707,16 @@ template <int SEG, bool OBS, bool XCOST>
 __device__ __forceinline__ void frx_tile_body(const FrxKernelArgs& A, const int cta_local, unsigned char* smem_raw) {
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
-    const int Mpad = A.Mpad, TP = A.tpitch;
+    const int Mpad = A.Mpad, TP = A.tpitch, MP = A.mpitch;
 #if FRX_TRACE
     bool traced = false;
 #endif
     FRX_STAMP(0);                                                            // kernel entry
     double* s_ref = reinterpret_cast<double*>(smem_raw);                    // [6][Mpad]
     double* s_Ttab = s_ref + 6 * Mpad;                                       // [FRX_MAX_T_VALUES]
-    double* s_memo = s_Ttab + FRX_MAX_T_VALUES;                              // [WARPS][SLOTS][M_FIELDS][TP]
-    FrxMemoHdr* s_hdr = reinterpret_cast<FrxMemoHdr*>(s_memo + (size_t)FRX_WARPS_PER_CTA * FRX_MEMO_SLOTS * M_FIELDS * TP);
+    double* s_tp = s_Ttab + FRX_MAX_T_VALUES;                                // [T_ROWS][TP] rounded powers of the step times
+    double* s_memo = s_tp + T_ROWS * TP;                                     // [WARPS][SLOTS][M_FIELDS][MP]
+    FrxMemoHdr* s_hdr = reinterpret_cast<FrxMemoHdr*>(s_memo + (size_t)FRX_WARPS_PER_CTA * FRX_MEMO_SLOTS * M_FIELDS * MP);
     unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_hdr + FRX_WARPS_PER_CTA * FRX_MEMO_SLOTS);
     FrxBest* s_best = reinterpret_cast<FrxBest*>(s_bar + 2);                 // [WARPS]
     double* s_rows = reinterpret_cast<double*>(s_best + FRX_WARPS_PER_CTA);  // [WARPS][32 * 13] sampling rows of a tile
@@ -736,11 +741,7 @@ __device__ __forceinline__ void frx_tile_body(const FrxKernelArgs& A, const int 
         s_Ttab[k] = (k < A.nT) ? A.Ttab[k] : __longlong_as_double(0x7ff8000000000000LL);
     __shared__ int s_Tlen[FRX_MAX_T_VALUES];
     for (int k = threadIdx.x; k < FRX_MAX_T_VALUES; k += FRX_THREADS) s_Tlen[k] = (k < A.nT) ? A.Tlen[k] : 0;
-    {   // the time-power tables are read by the first memo fill a few microseconds from now: start pulling them into L2
-        const char* tp = reinterpret_cast<const char*>(A.tpow);
-        const int lines = (A.nT * 5 * TP * (int)sizeof(double) + 127) / 128;
-        for (int k = threadIdx.x; k < lines; k += FRX_THREADS) asm volatile("prefetch.global.L2 [%0];" ::"l"(tp + (size_t)k * 128));
-    }
+    for (int k = threadIdx.x; k < T_ROWS * TP; k += FRX_THREADS) s_tp[k] = __ldg(A.tpow + k);     // visible after the barrier below
     if (lane < FRX_MEMO_SLOTS) s_hdr[wib * FRX_MEMO_SLOTS + lane].valid = 0;
     __shared__ unsigned int s_cnt[CNT_REASON1 + 10];     // per-CTA event counters
     __shared__ unsigned long long s_part[FRX_THREADS];   // last CTA: partial counter sums
@@ -788,7 +789,7 @@ __device__ __forceinline__ void frx_tile_body(const FrxKernelArgs& A, const int 
     __syncthreads();
 
     FRX_STAMP(1);                                                            // reference tables staged
-    double* memo = s_memo + (size_t)wib * FRX_MEMO_SLOTS * M_FIELDS * TP;
+    double* memo = s_memo + (size_t)wib * FRX_MEMO_SLOTS * M_FIELDS * MP;
     FrxMemoHdr* hdr = s_hdr + wib * FRX_MEMO_SLOTS;
     double best_cost = __longlong_as_double(0x7ff0000000000000LL);  // +inf
     long long best_idx = -1;
@@ -855,11 +856,11 @@ __device__ __forceinline__ void frx_tile_body(const FrxKernelArgs& A, const int 
             }
             if (sa < 0) {
                 sa = (sb == 0) ? 1 : 0;
-                frx_memo_fill(A, s_ref, s_Ttab, s_Tlen, FRX_TRW, memo + (size_t)sa * M_FIELDS * TP, hdr + sa, aT, as0, ass0, asss0, ass1);
+                frx_memo_fill(A, s_ref, s_Ttab, s_Tlen, s_tp, FRX_TRW, memo + (size_t)sa * M_FIELDS * MP, hdr + sa, aT, as0, ass0, asss0, ass1);
             }
             if (mB && sb < 0) {
                 sb = 1 - sa;
-                frx_memo_fill(A, s_ref, s_Ttab, s_Tlen, nullptr, memo + (size_t)sb * M_FIELDS * TP, hdr + sb, bT, bs0, bss0, bsss0, bss1);
+                frx_memo_fill(A, s_ref, s_Ttab, s_Tlen, s_tp, nullptr, memo + (size_t)sb * M_FIELDS * MP, hdr + sb, bT, bs0, bss0, bsss0, bss1);
             }
             __syncwarp();
             FRX_STAMP(3);                                                    // memo slots ready
@@ -868,8 +869,8 @@ __device__ __forceinline__ void frx_tile_body(const FrxKernelArgs& A, const int 
             o.ev = 0; o.total = 0.0; o.winner_ok = false; o.t_missing = false;
             if ((pass >> lane) & 1u) {
                 const int slot = ((mB >> lane) & 1u) ? sb : sa;
-                o = frx_candidate<SEG, OBS, XCOST>(A, cost_mask, pass, r, T, d0, dd0, ddd0, d1, dd1, ddd1, memo + (size_t)slot * M_FIELDS * TP,
-                                              hdr + slot);
+                o = frx_candidate<SEG, OBS, XCOST>(A, cost_mask, pass, r, T, d0, dd0, ddd0, d1, dd1, ddd1, memo + (size_t)slot * M_FIELDS * MP,
+                                              hdr + slot, s_tp);
             }
             __syncwarp();
             FRX_STAMP(4);                                                    // candidates of the pass evaluated

@@ -1,0 +1,447 @@
+// frx_obstacle.cuh -- the obstacle pass as kernels of its own (large plans; included by frx_kernels.cu): prediction cost
+// (collision_probability.py:264-299), distance to obstacles (partial_cost_functions.py:172-186), collision sweep
+// (planner.py:329-378, collision_check.py:110-200), then the weighted sum, the arg-min and the result record.
+//
+// Why split from the eval kernel: this pass is pure fp64 arithmetic on warp-uniform obstacle records.  Inside the eval
+// kernel it runs at 12 warps per SM (168 registers, 175 KB of shared memory per SM, ~50 KB of L1 left for the records);
+// here it needs almost no shared memory (the records live in a ~200 KB L1) and runs 16 warps per SM at 128 registers.
+//
+// Work unit = (64 candidates per warp: rows r and r + 256 of a thread, a CHUNK of the time steps).  One thread per
+// candidate, x / y / theta come back from the state planes, coalesced, loaded TWO steps ahead of their use.  Per step:
+//   * prediction cost: frx_pred_step -- 11 fp64 instructions per (candidate, obstacle) instead of 20;
+//   * collision: every lane builds its exact ego hull (obb-sum of boxes k, k + 1); the warp then culls the step's
+//     obstacle hulls COOPERATIVELY: the bounding box of the 32 ego hull circles comes from four REDUX min/max on
+//     order-preserving integer images of fp32 coordinates, lane o tests obstacle o against it (fp32, conservatively
+//     inflated: frx_cull_radius) and a ballot yields the few hulls any lane can touch.  Only those go through the
+//     per-lane exact fp64 circle test and the separating-axis test -- the same decisions as testing all of them, at
+//     ~1/5 of the instructions (50 obstacles: 400 -> 70 per lane and step).  Static boxes (road boundary) are culled the
+//     same way, so a wall costs one lane-test per warp and step instead of one per candidate and step.
+//
+// Step chunks: neither term couples the steps of a candidate (the prediction cost is a sum, the sweep only wants the
+// FIRST hit), so a plan that would leave the GPU with one or two long units per warp -- 200,000 rows are 1.3 units per
+// resident warp -- is cut into C chunks of steps: C times more units of 1/C the length, dealt round-robin, each writes
+// its partial sum and its first hits to scratch, and frx_obstacle_finish_kernel adds them up in chunk order (fixed
+// order: the result does not depend on scheduling).  A chunk that starts at step i0 > 0 evaluates step i0 - 1 for the
+// ego box only (the hull of boxes i0 - 1, i0 needs it).  Plans with >= 8 units per warp run one chunk and finish inline.
+#pragma once
+
+#define FRX_OBS_THREADS 256
+#ifndef FRX_OBS_ROWS
+#define FRX_OBS_ROWS 2
+#endif
+#define FRX_OBS_NOHIT 127u
+
+__device__ __forceinline__ int frx_f32_key(float f) {          // order-preserving float -> int
+    const int b = __float_as_int(f);
+    return b >= 0 ? b : (b ^ 0x7fffffff);
+}
+__device__ __forceinline__ float frx_key_f32(int k) { return __int_as_float(k >= 0 ? k : (k ^ 0x7fffffff)); }
+
+struct FrxObsAcc {      // what a thread carries to the end of the kernel
+    double best_cost;
+    long long best_idx;
+    unsigned n_col, n_bnd;
+};
+
+// one candidate: fill the cost terms this pass owns, weighted sum in name-sorted order (cost_function.py:78-91), flags,
+// running arg-min (planner.py:384-392: lowest row wins ties)
+__device__ __forceinline__ void frx_obs_row_finish(const FrxKernelArgs& A, const long long r, const uint32_t fl, const bool need_pred,
+                                                   const double pred_sum, const double d2o_sum, const bool collide, const int col_k,
+                                                   const bool boundary, const int bnd_k, FrxObsAcc& acc) {
+    const bool costed = (fl & FRX_FLAG_COSTED) != 0, candidate = (fl & FRX_FLAG_CANDIDATE) != 0;
+    double total = 0.0;
+    if (costed) {
+        double* cp = A.costs + (size_t)r * A.n_costs;
+        for (int k = 0; k < A.n_costs; ++k) {
+            const int id = A.cost_ids[k];
+            double cv;
+            if (id == FRX_COST_PREDICTION) { cv = need_pred ? pred_sum : 0.0; cp[k] = cv; }
+            else if (id == FRX_COST_DISTANCE_TO_OBSTACLES) { cv = d2o_sum; cp[k] = cv; }
+            else cv = cp[k];
+            total += A.w[k] * cv;
+        }
+        A.total[r] = total;
+    }
+    if (collide || boundary) {
+        uint32_t f2 = fl;
+        if (collide) { f2 |= FRX_FLAG_COLLIDE | ((uint32_t)col_k << FRX_FLAG_COLLIDE_STEP_SHIFT); ++acc.n_col; }
+        if (boundary) { f2 |= FRX_FLAG_BOUNDARY | ((uint32_t)bnd_k << FRX_FLAG_BOUNDARY_STEP_SHIFT); ++acc.n_bnd; }
+        A.flags[r] = f2;
+    }
+    if (candidate && !collide && !boundary && (total < acc.best_cost || (total == acc.best_cost && r < acc.best_idx))) {
+        acc.best_cost = total; acc.best_idx = r;
+    }
+}
+
+// block reduction of (min cost, lowest row) and the two counters of this pass; the last block finishes the plan: winners
+// of all blocks, counter rows of the eval kernel's CTAs (A.n_cta of them) plus this pass's two global counters, result
+// record + winner state rows to mapped host memory
+__device__ __forceinline__ void frx_obs_block_finish(const FrxKernelArgs& A, FrxObsAcc acc) {
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    constexpr int NW = FRX_OBS_THREADS / 32;
+    __shared__ FrxBest s_best[NW];
+    __shared__ unsigned int s_hits[2];
+    __shared__ unsigned long long s_part[FRX_OBS_THREADS];
+    __shared__ int s_is_last;
+    if (threadIdx.x < 2) s_hits[threadIdx.x] = 0u;
+    __syncthreads();
+    double best_cost = acc.best_cost;
+    long long best_idx = acc.best_idx;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const double oc = __shfl_xor_sync(FULL, best_cost, off);
+        const long long oi = __shfl_xor_sync(FULL, best_idx, off);
+        if (oi >= 0 && (best_idx < 0 || oc < best_cost || (oc == best_cost && oi < best_idx))) { best_cost = oc; best_idx = oi; }
+    }
+    const unsigned n_col = __reduce_add_sync(FULL, acc.n_col), n_bnd = __reduce_add_sync(FULL, acc.n_bnd);
+    if (lane == 0) {
+        s_best[wib].cost = best_cost; s_best[wib].idx = best_idx;
+        if (n_col) atomicAdd(&s_hits[0], n_col);
+        if (n_bnd) atomicAdd(&s_hits[1], n_bnd);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        FrxBest b = s_best[0];
+#pragma unroll
+        for (int w = 1; w < NW; ++w) {
+            FrxBest o = s_best[w];
+            if (o.idx >= 0 && (b.idx < 0 || o.cost < b.cost || (o.cost == b.cost && o.idx < b.idx))) b = o;
+        }
+        A.blockbest[blockIdx.x] = b;
+        if (s_hits[0]) atomicAdd(A.counters + CNT_COLLIDE, (unsigned long long)s_hits[0]);
+        if (s_hits[1]) atomicAdd(A.counters + CNT_BOUNDARY, (unsigned long long)s_hits[1]);
+        __threadfence();
+        unsigned long long done = atomicAdd(A.counters + CNT_DONE, 1ULL);
+        s_is_last = (done == (unsigned long long)(gridDim.x - 1));
+    }
+    __syncthreads();
+    if (!s_is_last) return;
+    __threadfence();
+    constexpr int NC = CNT_REASON1 + 10;
+    constexpr int NPART = FRX_OBS_THREADS / NC;
+    FrxBest b; b.cost = __longlong_as_double(0x7ff0000000000000LL); b.idx = -1;
+    for (int k = threadIdx.x; k < (int)gridDim.x; k += FRX_OBS_THREADS) {
+        FrxBest o;
+        o.cost = __ldcg(&A.blockbest[k].cost);
+        o.idx = __ldcg(&A.blockbest[k].idx);
+        if (o.idx >= 0 && (b.idx < 0 || o.cost < b.cost || (o.cost == b.cost && o.idx < b.idx))) b = o;
+    }
+    {
+        const int c = threadIdx.x % NC, part = threadIdx.x / NC;
+        unsigned long long a2 = 0;
+        if (part < NPART)
+            for (int k = part; k < A.n_cta; k += NPART) a2 += __ldcg(A.blockcnt + (size_t)k * NC + c);
+        s_part[threadIdx.x] = a2;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        FrxBest o;
+        o.cost = __shfl_xor_sync(FULL, b.cost, off);
+        o.idx = __shfl_xor_sync(FULL, b.idx, off);
+        if (o.idx >= 0 && (b.idx < 0 || o.cost < b.cost || (o.cost == b.cost && o.idx < b.idx))) b = o;
+    }
+    if (lane == 0) s_best[wib] = b;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        b = s_best[0];
+#pragma unroll
+        for (int w = 1; w < NW; ++w) {
+            FrxBest o = s_best[w];
+            if (o.idx >= 0 && (b.idx < 0 || o.cost < b.cost || (o.cost == b.cost && o.idx < b.idx))) b = o;
+        }
+        s_best[0] = b;
+        if (b.idx >= 0) b.idx += A.row_base;   // the winner record carries the GLOBAL row index
+        *A.winner = b;
+        A.host_res->winner = b;
+    } else if (threadIdx.x >= 32 && threadIdx.x < 32 + NC) {
+        const int c = threadIdx.x - 32;
+        unsigned long long tot = 0;
+        for (int q = 0; q < NPART; ++q) tot += s_part[q * NC + c];
+        if (c == CNT_COLLIDE || c == CNT_BOUNDARY) tot += atomicExch(A.counters + c, 0ULL);
+        A.host_res->counters[c] = tot;
+    } else if (threadIdx.x >= 64 && threadIdx.x < 64 + (FRX_NUM_COUNTERS - NC)) {
+        const int c = NC + (threadIdx.x - 64);
+        unsigned long long v = atomicExch(A.counters + c, 0ULL);
+        A.host_res->counters[c] = v;
+    }
+    __syncthreads();
+    const long long wi = s_best[0].idx;
+    const int Nt = A.Nt;
+    if (wi >= 0 && A.store_states) {
+        for (int q = threadIdx.x; q < FRX_NUM_FIELDS * Nt; q += FRX_OBS_THREADS) {
+            const int f = q / Nt, i = q - f * Nt;
+            A.host_res->winner_states[f][i] = __ldcg(A.states + frx_state_index(wi, Nt, FRX_NUM_FIELDS, f, i));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(FRX_OBS_THREADS, FRX_OBS_MIN_CTAS)
+frx_obstacle_kernel(const __grid_constant__ FrxKernelArgs A) {
+    const int lane = threadIdx.x & 31;
+    const int Nt = A.Nt;
+    const long long N = A.N;
+    constexpr size_t fstride = 32;                         // [block of 32 candidates][step][field][32], see frx_state_index
+    const size_t Np = (size_t)A.nf_store * 32;             // doubles between two steps of a candidate
+    __shared__ int s_npred[64], s_nhull[64];               // records per step (Nt <= 64)
+    for (int k = threadIdx.x; k < 64; k += FRX_OBS_THREADS) {
+        s_npred[k] = (A.O > 0 && k < A.Tp) ? A.on_pred[k] : 0;
+        s_nhull[k] = (A.O > 0 && k < A.Tp) ? A.on_hull[k] : 0;
+    }
+    __syncthreads();
+    unsigned cost_mask = 0;
+    for (int k = 0; k < A.n_costs; ++k) cost_mask |= 1u << A.cost_ids[k];
+    const bool pred_on = (cost_mask & (1u << FRX_COST_PREDICTION)) && A.O > 0;
+    const bool d2o_on = (cost_mask & (1u << FRX_COST_DISTANCE_TO_OBSTACLES)) && A.n_obs_pos > 0;
+    const bool col_on = A.check_collisions && (A.O > 0 || A.B > 0);
+    const double ox = A.origin_x, oy = A.origin_y;
+    FrxObsAcc acc;
+    acc.best_cost = __longlong_as_double(0x7ff0000000000000LL); acc.best_idx = -1; acc.n_col = acc.n_bnd = 0;
+    constexpr int R = FRX_OBS_ROWS;
+    const int C = A.obs_chunks;                            // step chunks (1: finish inline)
+    const int clen = (Nt + C - 1) / C;
+    const long long row_blocks = (N + (long long)R * FRX_OBS_THREADS - 1) / ((long long)R * FRX_OBS_THREADS);
+    const long long n_units = row_blocks * C;
+    // the trip count is uniform over the block: every warp-synchronous step below is reached by all 32 lanes
+    for (long long unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+        const long long b0 = (unit / C) * R * FRX_OBS_THREADS;
+        const int chunk = (int)(unit % C);
+        const int i0 = chunk * clen, i1 = (i0 + clen < Nt) ? (i0 + clen) : Nt;
+        long long rr_[R];
+        uint32_t fl[R];
+        bool need_pred[R], need_col[R], need_d2o[R], live[R];
+        bool any_pred = false, any_col = false, any_d2o = false;
+#pragma unroll
+        for (int u = 0; u < R; ++u) {
+            const long long r = b0 + (long long)u * FRX_OBS_THREADS + threadIdx.x;
+            live[u] = r < N;
+            rr_[u] = live[u] ? r : (N - 1);
+            fl[u] = live[u] ? A.flags[rr_[u]] : 0u;
+            const bool costed = (fl[u] & FRX_FLAG_COSTED) != 0, candidate = (fl[u] & FRX_FLAG_CANDIDATE) != 0;
+            need_pred[u] = costed && pred_on; need_d2o[u] = costed && d2o_on; need_col[u] = candidate && col_on;
+            any_pred |= need_pred[u]; any_col |= need_col[u]; any_d2o |= need_d2o[u];
+        }
+        double pred_sum[R], d2o_sum[R];
+        bool collide[R], boundary[R];
+        int col_k[R], bnd_k[R];          // ego hull index of the first hit (planner.py:370-372 reads the velocity there)
+#pragma unroll
+        for (int u = 0; u < R; ++u) { pred_sum[u] = 0.0; d2o_sum[u] = 0.0; collide[u] = false; boundary[u] = false; col_k[u] = bnd_k[u] = 0; }
+        const bool w_pred = __any_sync(FULL, any_pred), w_col = __any_sync(FULL, any_col), w_d2o = __any_sync(FULL, any_d2o);
+        if ((w_pred || w_d2o || w_col) && i0 < i1) {
+            double pbx[R], pby[R], pux[R], puy[R];   // ego box of the previous step
+            const double* q[R];
+            double x1[R], y1[R], t1[R], x2[R], y2[R], t2[R];     // steps i + 1 and i + 2, in flight
+            // a later chunk starts one step early: that step only yields the ego box the first hull needs
+            const int ifirst = (i0 > 0 && w_col) ? (i0 - 1) : i0;
+#pragma unroll
+            for (int u = 0; u < R; ++u) {
+                pbx[u] = pby[u] = pux[u] = puy[u] = 0.0;
+                q[u] = A.states + frx_state_index(rr_[u], Nt, A.nf_store, 0, ifirst);
+                x1[u] = __ldcg(q[u]); y1[u] = __ldcg(q[u] + fstride); t1[u] = w_col ? __ldcg(q[u] + 2 * fstride) : 0.0;
+                x2[u] = y2[u] = t2[u] = 0.0;
+                if (ifirst + 1 < i1) {
+                    x2[u] = __ldcg(q[u] + Np); y2[u] = __ldcg(q[u] + Np + fstride);
+                    if (w_col) t2[u] = __ldcg(q[u] + Np + 2 * fstride);
+                }
+            }
+            for (int i = ifirst; i < i1; ++i) {
+                double x[R], y[R], th[R];
+#pragma unroll
+                for (int u = 0; u < R; ++u) {
+                    x[u] = x1[u]; y[u] = y1[u]; th[u] = t1[u];
+                    x1[u] = x2[u]; y1[u] = y2[u]; t1[u] = t2[u];
+                    if (i + 2 < i1) {
+                        x2[u] = __ldcg(q[u] + 2 * Np); y2[u] = __ldcg(q[u] + 2 * Np + fstride);
+                        if (w_col) t2[u] = __ldcg(q[u] + 2 * Np + 2 * fstride);
+                    }
+                    q[u] += Np;
+                }
+                const bool warm = i < i0;                   // box-only step in front of a later chunk
+                if (w_pred && i >= 1 && !warm)
+                    frx_pred_step<R>(A.opred + (size_t)(i - 1) * A.O * FRX_PRED_REC, s_npred[i - 1], x, y, need_pred, pred_sum);
+                if (w_d2o && !warm) {
+#pragma unroll
+                    for (int u = 0; u < R; ++u) {
+                        if (need_d2o[u]) {
+                            for (int o = 0; o < A.n_obs_pos; ++o) {
+                                double ex = x[u] - __ldg(A.obs_pos + 2 * o), ey = y[u] - __ldg(A.obs_pos + 2 * o + 1);
+                                double dist = sqrt(ex * ex + ey * ey);
+                                d2o_sum[u] += ddivg(1.0, dist * dist);
+                            }
+                        }
+                    }
+                }
+                if (!w_col) continue;
+#pragma unroll
+                for (int u = 0; u < R; ++u) {
+                    // lanes that still have something to find; the set only shrinks, so a warp without one is done with
+                    // the sweep of this unit for good
+                    const bool act = need_col[u] && !(collide[u] && (boundary[u] || A.B == 0));
+                    if (!__any_sync(FULL, act)) continue;
+                    double sn, cs;
+                    sincos(th[u], &sn, &cs);
+                    const double bx = x[u] + A.wb_rear * cs, by = y[u] + A.wb_rear * sn;     // state.py:30-39 rear axle -> centre
+                    if (i >= 1 && !warm) {
+                        const int k = i - 1;                                            // hull of boxes k, k + 1
+                        Hull e = obb_sum_hull(pbx[u], pby[u], pux[u], puy[u], bx, by, cs, sn, A.half_len, A.half_wid);
+                        const double er = sqrt(e.ha * e.ha + e.hb * e.hb) * (1.0 + 1e-9);
+                        // ---- warp bounding box of the active lanes' hull circles (fp32, inflated; frx_cull_radius)
+                        const double rx = e.cx - ox, ry = e.cy - oy;
+                        const float fx = (float)rx, fy = (float)ry, fr = frx_cull_radius(er, rx, ry);
+                        const int kx0 = __reduce_min_sync(FULL, act ? frx_f32_key(fx - fr) : 0x7fffffff);
+                        const int kx1 = __reduce_max_sync(FULL, act ? frx_f32_key(fx + fr) : (int)0x80000000);
+                        const int ky0 = __reduce_min_sync(FULL, act ? frx_f32_key(fy - fr) : 0x7fffffff);
+                        const int ky1 = __reduce_max_sync(FULL, act ? frx_f32_key(fy + fr) : (int)0x80000000);
+                        // one more ulp-scale pad for the roundings of fx -+ fr and of the centre / half-extent below
+                        const float bx0 = frx_key_f32(kx0), bx1 = frx_key_f32(kx1), by0 = frx_key_f32(ky0), by1 = frx_key_f32(ky1);
+                        float mx = 0.5f * (bx0 + bx1), my = 0.5f * (by0 + by1);
+                        const float pad = 1e-6f * (fabsf(bx0) + fabsf(bx1) + fabsf(by0) + fabsf(by1)) + 1e-4f;
+                        float hx = 0.5f * (bx1 - bx0) + pad, hy = 0.5f * (by1 - by0) + pad;
+                        // a non-finite hull (cannot come out of finite inputs) must not hide anything from the exact test
+                        if (__any_sync(FULL, act && !(fabsf(fx) + fabsf(fy) + fr < 3e38f))) {
+                            mx = my = 0.f; hx = hy = __int_as_float(0x7f800000);
+                        }
+                        if (k >= 1 && __any_sync(FULL, act && !collide[u])) {
+                            // obstacle hulls of step k - 1 (hull record: cx, cy, r | ux, uy | ha, hb)
+                            const int n = s_nhull[k - 1];
+                            const float4* __restrict__ c32 = A.ohull32 + (size_t)(k - 1) * A.O;
+                            const double2* __restrict__ rec = reinterpret_cast<const double2*>(A.ohull + (size_t)(k - 1) * A.O * 8);
+                            for (int o0 = 0; o0 < n; o0 += 32) {
+                                bool near = false;
+                                if (o0 + lane < n) {
+                                    const float4 c = __ldg(c32 + o0 + lane);
+                                    near = (fabsf(c.x - mx) <= hx + c.z) && (fabsf(c.y - my) <= hy + c.z);
+                                }
+                                unsigned wm = __ballot_sync(FULL, near);
+                                while (wm) {                                  // warp-uniform: the hulls some lane may touch
+                                    const int o = o0 + __ffs(wm) - 1;
+                                    wm &= wm - 1;
+                                    if (act && !collide[u]) {
+                                        const double2 cc = __ldg(rec + 4 * o);
+                                        const double hr = __ldg(reinterpret_cast<const double*>(rec + 4 * o + 1));
+                                        const double rr = er + hr;
+                                        const double ddx = cc.x - e.cx, ddy = cc.y - e.cy;
+                                        if (!(ddx * ddx + ddy * ddy > rr * rr)) {
+                                            const double2 ru = __ldg(rec + 4 * o + 1), uh = __ldg(rec + 4 * o + 2);
+                                            if (obb_overlap(e, cc.x, cc.y, ru.y, uh.x, uh.y, __ldg(reinterpret_cast<const double*>(rec + 4 * o + 3)))) {
+                                                collide[u] = true; col_k[u] = k;
+                                            }
+                                        }
+                                    }
+                                }
+                            }
+                        }
+                        if (A.B > 0 && __any_sync(FULL, act && !boundary[u])) {
+                            for (int b0s = 0; b0s < A.B; b0s += 32) {
+                                bool near = false;
+                                if (b0s + lane < A.B) {
+                                    const float4 c = __ldg(A.sobb32 + b0s + lane);
+                                    near = (fabsf(c.x - mx) <= hx + c.z) && (fabsf(c.y - my) <= hy + c.z);
+                                }
+                                unsigned wm = __ballot_sync(FULL, near);
+                                while (wm) {
+                                    const int b = b0s + __ffs(wm) - 1;
+                                    wm &= wm - 1;
+                                    if (act && !boundary[u]) {
+                                        const double* __restrict__ sb = A.sobb + b * 8;
+                                        const double rr = er + __ldg(sb + 6);
+                                        const double ddx = __ldg(sb) - e.cx, ddy = __ldg(sb + 1) - e.cy;
+                                        if (!(ddx * ddx + ddy * ddy > rr * rr) &&
+                                            obb_overlap(e, __ldg(sb), __ldg(sb + 1), __ldg(sb + 2), __ldg(sb + 3), __ldg(sb + 4), __ldg(sb + 5))) {
+                                            boundary[u] = true; bnd_k[u] = k;
+                                        }
+                                    }
+                                }
+                            }
+                        }
+                    }
+                    pbx[u] = bx; pby[u] = by; pux[u] = cs; puy[u] = sn;
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < R; ++u) {
+            if (!live[u]) continue;
+            if (C == 1) {
+                frx_obs_row_finish(A, rr_[u], fl[u], need_pred[u], pred_sum[u], d2o_sum[u], collide[u], col_k[u], boundary[u],
+                                   bnd_k[u], acc);
+            } else {
+                // partial results of this chunk: frx_obstacle_finish_kernel combines them in chunk order
+                const size_t slot = (size_t)chunk * (size_t)N + (size_t)rr_[u];
+                A.obs_part[slot] = pred_sum[u];
+                A.obs_hit[slot] = (collide[u] ? (uint32_t)col_k[u] : FRX_OBS_NOHIT) | ((boundary[u] ? (uint32_t)bnd_k[u] : FRX_OBS_NOHIT) << 8);
+            }
+        }
+    }
+    if (C == 1) frx_obs_block_finish(A, acc);
+}
+
+// chunked plans: add the partial sums up in chunk order, earliest hit over the chunks, then the same finish as the
+// one-chunk kernel (grid-stride over the rows, one thread per candidate)
+__global__ void __launch_bounds__(FRX_OBS_THREADS)
+frx_obstacle_finish_kernel(const __grid_constant__ FrxKernelArgs A) {
+    const long long N = A.N;
+    const int C = A.obs_chunks;
+    unsigned cost_mask = 0;
+    for (int k = 0; k < A.n_costs; ++k) cost_mask |= 1u << A.cost_ids[k];
+    const bool pred_on = (cost_mask & (1u << FRX_COST_PREDICTION)) && A.O > 0;
+    FrxObsAcc acc;
+    acc.best_cost = __longlong_as_double(0x7ff0000000000000LL); acc.best_idx = -1; acc.n_col = acc.n_bnd = 0;
+    for (long long r = (long long)blockIdx.x * FRX_OBS_THREADS + threadIdx.x; r < N; r += (long long)gridDim.x * FRX_OBS_THREADS) {
+        const uint32_t fl = A.flags[r];
+        double pred = 0.0;
+        uint32_t ck = FRX_OBS_NOHIT, bk = FRX_OBS_NOHIT;
+        for (int c = 0; c < C; ++c) {
+            const size_t slot = (size_t)c * (size_t)N + (size_t)r;
+            pred += __ldcg(A.obs_part + slot);
+            const uint32_t h = __ldcg(A.obs_hit + slot);
+            ck = min(ck, h & 0xffu); bk = min(bk, (h >> 8) & 0xffu);
+        }
+        frx_obs_row_finish(A, r, fl, (fl & FRX_FLAG_COSTED) && pred_on, pred, 0.0, ck != FRX_OBS_NOHIT, (int)ck, bk != FRX_OBS_NOHIT,
+                           (int)bk, acc);
+    }
+    frx_obs_block_finish(A, acc);
+}
+
+// How many step chunks: enough units for >= 4 per resident warp, at least 4 steps per chunk; FRX_OBS_CHUNKS overrides
+// (tests pin 1 to compare with the fused pass bit for bit).  The distance-to-obstacles term keeps one chunk.
+static int frx_obstacle_chunks(const FrxKernelArgs& a, long long warps_resident) {
+    if (a.obs_part == nullptr || a.obs_hit == nullptr) return 1;     // no scratch reserved (very large plans)
+    if (const char* e = getenv("FRX_OBS_CHUNKS")) {
+        const int f = atoi(e);
+        if (f >= 1 && f <= 16) return (f < a.Nt) ? f : 1;
+    }
+    for (int k = 0; k < a.n_costs; ++k)
+        if (a.cost_ids[k] == FRX_COST_DISTANCE_TO_OBSTACLES && a.n_obs_pos > 0) return 1;
+    const long long units = (a.N + 32 * FRX_OBS_ROWS - 1) / (32 * FRX_OBS_ROWS);
+    int c = 1;
+    while (c < 8 && units * c < 4 * warps_resident && (a.Nt + 2 * c - 1) / (2 * c) >= 4) c *= 2;
+    return c;
+}
+
+// scratch the chunked pass needs (elements of obs_part / obs_hit)
+size_t frx_obstacle_scratch_elems(long long N) { return (size_t)8 * (size_t)N; }
+
+cudaError_t frx_launch_obstacle_pass(FrxKernelArgs& a, int sm_count, cudaStream_t st, int* launches) {
+    static thread_local int occ = 0;
+    if (occ == 0) {
+        cudaFuncSetAttribute(frx_obstacle_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 4);   // 8 KB shared, the rest L1
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, frx_obstacle_kernel, FRX_OBS_THREADS, 0) != cudaSuccess || occ < 1) occ = 1;
+        if (getenv("FRX_DEBUG")) fprintf(stderr, "[frx] obstacle kernel: %d blocks of %d threads per SM\n", occ, FRX_OBS_THREADS);
+    }
+    const long long full = (long long)sm_count * occ;
+    a.obs_chunks = frx_obstacle_chunks(a, full * (FRX_OBS_THREADS / 32));
+    const long long row_blocks = (a.N + FRX_OBS_THREADS * FRX_OBS_ROWS - 1) / (FRX_OBS_THREADS * FRX_OBS_ROWS);
+    const long long want = row_blocks * a.obs_chunks;
+    const int grid = (int)(want < full ? want : full);
+    frx_obstacle_kernel<<<grid, FRX_OBS_THREADS, 0, st>>>(a);
+    *launches = 1;
+    if (a.obs_chunks > 1) {
+        long long fg = (a.N + FRX_OBS_THREADS - 1) / FRX_OBS_THREADS;
+        if (fg > (long long)sm_count * 8) fg = (long long)sm_count * 8;
+        frx_obstacle_finish_kernel<<<(int)fg, FRX_OBS_THREADS, 0, st>>>(a);
+        *launches = 2;
+    }
+    return cudaGetLastError();
+}
+int frx_obstacle_pass_max_grid(int sm_count) { return sm_count * 8; }
+

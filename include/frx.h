@@ -80,6 +80,13 @@ enum {
 #define FRX_FLAG_IN_LIST (1u << 15)   /* member of trajectories_all */
 #define FRX_FLAG_COSTED (1u << 16)    /* cost function evaluated */
 #define FRX_FLAG_CANDIDATE (1u << 17) /* handed to the collision check / arg-min */
+/* index k of the first ego hull (obb-sum of boxes k, k + 1; time index t0 + k) that met a predicted obstacle / a static box:
+ * what pycrcc's trajectories_collision_static_obstacles returns as "leaving_road_at" (planner.py:362-372, where the
+ * velocity at that index feeds boundary_harm).  Valid when FRX_FLAG_COLLIDE / FRX_FLAG_BOUNDARY is set. */
+#define FRX_FLAG_COLLIDE_STEP_SHIFT 18
+#define FRX_FLAG_BOUNDARY_STEP_SHIFT 24
+#define FRX_FLAG_COLLIDE_STEP(f) (((f) >> FRX_FLAG_COLLIDE_STEP_SHIFT) & 63u)
+#define FRX_FLAG_BOUNDARY_STEP(f) (((f) >> FRX_FLAG_BOUNDARY_STEP_SHIFT) & 63u)
 
 /* cost term ids, alphabetical like the reference's evaluation order */
 enum {

@@ -446,25 +446,30 @@ static void ego_hulls(const env_t* E, const double* st, hull_t* eh) {
         eh[k] = obb_sum_hull(cx[k], cy[k], th[k], cx[k + 1], cy[k + 1], th[k + 1], P->length / 2, P->width / 2);
 }
 
+/* index k of the first ego hull that meets a predicted obstacle's hull k - 1, -1 if none (the time index pycrcc reports) */
 static int collides_predictions(const env_t* E, const hull_t* eh) {
     const int Nt = E->p->N + 1;
+    int first = -1;
     for (int o = 0; o < E->O; o++) {
         int L = E->olen[o] < Nt ? E->olen[o] : Nt;
         if (L <= 2) continue;
         int kmax = (Nt - 2 < L - 1) ? Nt - 2 : L - 1;
+        if (first >= 0 && kmax >= first) kmax = first - 1;
         for (int k = 1; k <= kmax; k++)
-            if (obb_overlap(&eh[k], &E->ohull[(size_t)o * E->T + (k - 1)])) return 1;
+            if (obb_overlap(&eh[k], &E->ohull[(size_t)o * E->T + (k - 1)])) { first = k; break; }
     }
-    return 0;
+    return first;
 }
 
 static int collides_static(const env_t* E, const hull_t* eh) {
     const int Nt = E->p->N + 1;
     for (int k = 0; k < Nt - 1; k++)
         for (int b = 0; b < E->B; b++)
-            if (obb_overlap(&eh[k], &E->sobb[b])) return 1;
-    return 0;
+            if (obb_overlap(&eh[k], &E->sobb[b])) return k;
+    return -1;
 }
+#define COLLIDE_BITS(k) (FLAG_COLLIDE | ((uint32_t)(k) << 18))
+#define BOUNDARY_BITS(k) (FLAG_BOUNDARY | ((uint32_t)(k) << 24))
 
 typedef struct { double cost; int64_t idx; } key_t2;
 static int key_cmp(const void* a, const void* b) {
@@ -549,8 +554,9 @@ int orc_plan(const orc_params* P, int64_t n, const double* sampling, int M, cons
                 fl |= FLAG_CANDIDATE;
                 if (check_all) {
                     ego_hulls(&E, st, eh);
-                    if (do_pred && collides_predictions(&E, eh)) fl |= FLAG_COLLIDE;
-                    if (B > 0 && collides_static(&E, eh)) fl |= FLAG_BOUNDARY;
+                    const int hk = do_pred ? collides_predictions(&E, eh) : -1, bk = (B > 0) ? collides_static(&E, eh) : -1;
+                    if (hk >= 0) fl |= COLLIDE_BITS(hk);
+                    if (bk >= 0) fl |= BOUNDARY_BITS(bk);
                 }
             }
             total[r] = tot; flags[r] = fl; traj_len[r] = tl;
@@ -605,10 +611,10 @@ int orc_plan(const orc_params* P, int64_t n, const double* sampling, int M, cons
                 memcpy(stx + F_THETA * Nt, xyth + (size_t)r * 3 * Nt + 2 * Nt, sizeof(double) * Nt);
             }
             ego_hulls(&E, stx, eh);
-            hit = do_pred ? collides_predictions(&E, eh) : 0;
-            off = (B > 0) ? collides_static(&E, eh) : 0;
-            if (hit) flags[r] |= FLAG_COLLIDE;
-            if (off) flags[r] |= FLAG_BOUNDARY;
+            const int hk = do_pred ? collides_predictions(&E, eh) : -1, bk = (B > 0) ? collides_static(&E, eh) : -1;
+            hit = hk >= 0; off = bk >= 0;
+            if (hit) flags[r] |= COLLIDE_BITS(hk);
+            if (off) flags[r] |= BOUNDARY_BITS(bk);
         }
         if (hit) res->collision_counter++;
         if (!hit && !off) { res->argmin = r; res->min_cost = total[r]; break; }

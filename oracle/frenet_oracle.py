@@ -55,6 +55,7 @@ def reason_bit(r: int) -> int:
     return 1 << (1 + r)
 FLAG_COLLIDE = 1 << 12
 FLAG_BOUNDARY = 1 << 13
+COLLIDE_STEP_SHIFT, BOUNDARY_STEP_SHIFT = 18, 24      # 6-bit index of the first colliding ego hull (include/frx.h)
 FLAG_STORED = 1 << 14      # reached reactive_planner.py:551-567 (has .cartesian/.curvilinear)
 FLAG_IN_LIST = 1 << 15     # member of `trajectories_all`
 FLAG_COSTED = 1 << 16      # cost function was evaluated for it
@@ -599,6 +600,34 @@ def collides_with_predictions(st, prm: Params, predictions, Nt):
     return False
 
 
+def first_collision_step(st, prm: Params, predictions, Nt):
+    """Index k of the first ego hull (time index t0 + k) that meets a predicted obstacle, -1 if none: what a pycrcc
+    time-variant collision query reports; same pairs as :func:`collides_with_predictions`."""
+    x, y, th = st[F_X], st[F_Y], st[F_THETA]
+    hl, hw = prm.length / 2, prm.width / 2
+    cx = x + prm.wb_rear_axle * np.cos(th)
+    cy = y + prm.wb_rear_axle * np.sin(th)
+    first = -1
+    for pred in predictions:
+        pos = np.asarray(pred["pos_list"], dtype=float)
+        L = min(Nt, len(pos))
+        if L <= 2:
+            continue
+        ori = np.asarray(pred["orientation_list"], dtype=float)
+        ohl, ohw = pred["shape"]["length"] / 2, pred["shape"]["width"] / 2
+        kmax = min(Nt - 2, L - 1)
+        if first >= 0:
+            kmax = min(kmax, first - 1)
+        for k in range(1, kmax + 1):
+            j = k - 1
+            e = obb_sum_hull(cx[k], cy[k], th[k], cx[k + 1], cy[k + 1], th[k + 1], hl, hw)
+            oh = obb_sum_hull(pos[j, 0], pos[j, 1], ori[j], pos[j + 1, 0], pos[j + 1, 1], ori[j + 1], ohl, ohw)
+            if obb_overlap(e, oh):
+                first = k
+                break
+    return first
+
+
 def collides_with_static(st, prm: Params, static_obbs, Nt):
     """Road-boundary stand-in (planner.py:362-378): ego hulls vs caller-provided static boxes
     [[cx, cy, theta, half_len, half_wid], ...].  Returns first colliding step or -1."""
@@ -687,12 +716,13 @@ def plan(sampling: np.ndarray, ref: RefPath, prm: Params, predictions: Sequence[
     collision_counter = 0
     for r in order:
         st = states[:, r, :]
-        hit = collides_with_predictions(st, prm, predictions, Nt) if (len(predictions) and collision_check) else False
-        off = collides_with_static(st, prm, static_obbs, Nt) != -1
+        hit_k = first_collision_step(st, prm, predictions, Nt) if (len(predictions) and collision_check) else -1
+        off_k = collides_with_static(st, prm, static_obbs, Nt)
+        hit, off = hit_k >= 0, off_k >= 0
         if hit:
-            flags[r] |= FLAG_COLLIDE
+            flags[r] |= FLAG_COLLIDE | (hit_k << COLLIDE_STEP_SHIFT)
         if off:
-            flags[r] |= FLAG_BOUNDARY
+            flags[r] |= FLAG_BOUNDARY | (off_k << BOUNDARY_STEP_SHIFT)
         if winner < 0:
             if hit:
                 collision_counter += 1

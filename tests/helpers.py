@@ -114,6 +114,12 @@ def compare_with_oracle(dev, ora, prm, tol=1e-6, check_collide=True, band=BAND):
     diff[~ok] = 0
     assert not diff.any(), f"{int((diff != 0).sum())} flag mismatches, first rows {np.nonzero(diff)[0][:5]}, " \
                            f"bits {[hex(int(x)) for x in diff[np.nonzero(diff)[0][:5]]]}"
+    if check_collide:
+        # index of the first colliding ego hull (feeds boundary_harm, planner.py:370-372): exact wherever a hit is flagged
+        for flag, shift in ((fo.FLAG_COLLIDE, fo.COLLIDE_STEP_SHIFT), (fo.FLAG_BOUNDARY, fo.BOUNDARY_STEP_SHIFT)):
+            hit = ((fl_o & np.uint64(flag)) != 0) & ok
+            kd, ko = (fl_d[hit] >> np.uint64(shift)) & np.uint64(63), (fl_o[hit] >> np.uint64(shift)) & np.uint64(63)
+            assert np.array_equal(kd, ko), f"first-hit hull index differs for flag {flag:#x}: rows {np.flatnonzero(hit)[kd != ko][:5]}"
     stored = ((fl_o & np.uint64(fo.FLAG_STORED)) != 0) & ok
     costed = ((fl_o & np.uint64(fo.FLAG_COSTED)) != 0) & ok
     errs = {}

@@ -131,6 +131,7 @@ def test_split_obstacle_kernel_equals_fused_pass(name, monkeypatch):
     g, ref, prm, preds = load_golden(name)
     S = np.ascontiguousarray(np.tile(g["sampling"], (4, 1))[:g["sampling"].shape[0] * 3 + 11])
     monkeypatch.setenv("FRX_SEG", "1")
+    monkeypatch.setenv("FRX_OBS_CHUNKS", "1")          # one step chunk: same summation order as the fused pass
     monkeypatch.setenv("FRX_SPLIT_OBS", "0")
     fused = device_plan(S, ref, prm, preds)
     monkeypatch.setenv("FRX_SPLIT_OBS", "1")
@@ -142,3 +143,29 @@ def test_split_obstacle_kernel_equals_fused_pass(name, monkeypatch):
     assert fused["res"].n_collide == split["res"].n_collide and fused["res"].n_boundary == split["res"].n_boundary
     assert np.array_equal(fused["handler"].winner_states(), split["handler"].winner_states())
     compare_with_oracle(split, fo.plan(S, ref, prm, preds), prm)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("chunks", [2, 4, 8])
+@pytest.mark.parametrize("name", ["arc_hv_draw_pred", "tjunction_draw", "tjunction_nodraw"])
+def test_step_chunked_obstacle_pass(name, chunks, monkeypatch):
+    """Mid-size plans cut the obstacle pass into chunks of time steps (frx_obstacle.cuh): masks, first-hit indices, counters
+    and the selected row equal the one-chunk pass exactly; the prediction cost is the same sum in a different association
+    (<= 1e-12 relative); the oracle contract holds."""
+    g, ref, prm, preds = load_golden(name)
+    S = np.ascontiguousarray(np.tile(g["sampling"], (4, 1))[:g["sampling"].shape[0] * 3 + 11])
+    walls = np.array([[float(np.mean(ref.ref_x[:40])), float(np.mean(ref.ref_y[:40])) + 6.0, 0.3, 30.0, 0.1]])
+    monkeypatch.setenv("FRX_SEG", "1")
+    monkeypatch.setenv("FRX_SPLIT_OBS", "1")
+    monkeypatch.setenv("FRX_OBS_CHUNKS", "1")
+    one = device_plan(S, ref, prm, preds, static_obbs=walls)
+    monkeypatch.setenv("FRX_OBS_CHUNKS", str(chunks))
+    cut = device_plan(S, ref, prm, preds, static_obbs=walls)
+    assert cut["res"].obstacle_kernel_ms > 0
+    for k in ("flags", "traj_len", "states", "reason_counts"):
+        assert np.array_equal(one[k], cut[k]), k
+    assert rel_err(cut["costs"], one["costs"]) < 1e-12 and rel_err(cut["total"], one["total"]) < 1e-12
+    for k in ("argmin", "n_in_list", "n_feasible", "collision_counter"):
+        assert one[k] == cut[k], k
+    assert one["res"].n_collide == cut["res"].n_collide and one["res"].n_boundary == cut["res"].n_boundary
+    compare_with_oracle(cut, fo.plan(S, ref, prm, preds, static_obbs=walls), prm)
