@@ -28,6 +28,7 @@ FLAG_STORED = 1 << 14
 FLAG_IN_LIST = 1 << 15
 FLAG_COSTED = 1 << 16
 FLAG_CANDIDATE = 1 << 17
+FLAG_COLLIDE_STEP_SHIFT, FLAG_BOUNDARY_STEP_SHIFT = 18, 24     # 6-bit index of the first colliding ego hull (frx.h)
 
 
 def flag_reason(r: int) -> int:
@@ -151,6 +152,8 @@ class Handler:
         self.n_rows = 0
         self.n_costs = 0
         self.Nt = 0
+        self.generation = 0       # bumped by every plan*: lazy views of an older plan (TrajectoryBundle) detect that the
+                                  # device buffers they point at have been recycled
 
     def close(self):
         if getattr(self, "_ctx", None):
@@ -247,18 +250,21 @@ class Handler:
         if sampling.ndim != 2 or sampling.shape[1] != 13:
             raise ValueError("sampling matrix must be [N, 13]")
         res = FrxResult()
+        self.generation += 1
         self._check(self._lib.frx_plan(self._ctx, sampling.shape[0], _dptr(sampling), int(row_index_base), C.byref(res)))
         self.n_rows = sampling.shape[0]
         return res
 
     def plan_device(self, device_ptr: int, n_rows: int, row_index_base: int = 0) -> FrxResult:
         res = FrxResult()
+        self.generation += 1
         self._check(self._lib.frx_plan_device(self._ctx, int(n_rows), C.c_void_p(device_ptr), int(row_index_base), C.byref(res)))
         self.n_rows = int(n_rows)
         return res
 
     def plan_device_async(self, device_ptr: int, n_rows: int, row_index_base: int = 0) -> None:
         """Enqueue only; pair with :meth:`plan_wait`."""
+        self.generation += 1
         self._check(self._lib.frx_plan_device_async(self._ctx, int(n_rows), C.c_void_p(device_ptr), int(row_index_base)))
         self.n_rows = int(n_rows)
 
@@ -274,6 +280,7 @@ class Handler:
         if row_count is None:
             row_count = total - row_first
         res = FrxResult()
+        self.generation += 1
         self._check(self._lib.frx_plan_grid(self._ctx, t1.size, _dptr(t1), ss1.size, _dptr(ss1), d1.size, _dptr(d1),
                                             _dptr(xcl), int(row_first), int(row_count), C.byref(res)))
         self.n_rows = int(row_count)
@@ -386,6 +393,8 @@ def plan_batched(handlers: Sequence["Handler"], samplings: Sequence[np.ndarray])
     rows = (C.c_int64 * n)(*[S.shape[0] for S in mats])
     ptrs = (C.POINTER(C.c_double) * n)(*[_dptr(S) for S in mats])
     res = (FrxResult * n)()
+    for h in handlers:
+        h.generation += 1
     rc = lib.frx_plan_batched(n, ctxs, rows, ptrs, res)
     if rc != 0:
         msg = lib.frx_last_error(handlers[0]._ctx)

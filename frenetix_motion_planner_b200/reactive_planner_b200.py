@@ -322,22 +322,33 @@ class ReactivePlannerB200:
         if "distance_to_obstacles" in self.cost_names:
             h.set_obstacle_positions(getattr(self, "obstacle_positions", None))
 
-    def _sampling_matrix(self, samp_level: int) -> np.ndarray:
+    def _level_axes(self, samp_level: int):
+        """The (t1, ss1, d1) axes of a sampling level as arrays in the reference's set-iteration order: the candidates are
+        their cartesian product with t1 slowest and d1 fastest, which is the loop nest of reactive_planner.py:149-158 (row
+        index == the reference's uniqueId) and the row order of generate_sampling_matrix (reactive_planner_cpp.py:228-253)."""
         t_set, v_set, d_set = sampling_axes(self.sampling_handler, samp_level, self.x_cl,
                                             cpp_style=(self.sampling_style == "cpp"))
-        return python_path_rows(t_set, v_set, d_set, self.x_cl)
+        return (np.fromiter(t_set, dtype=np.float64), np.fromiter(v_set, dtype=np.float64),
+                np.fromiter(d_set, dtype=np.float64))
 
-    def _prepare_level(self, samp_level: int) -> np.ndarray:
-        """Host work of one sampling level: the matrix and the time tables of its durations."""
-        sampling = self._sampling_matrix(samp_level)
-        self._total_count = sampling.shape[0]
+    def _sampling_matrix(self, samp_level: int) -> np.ndarray:
+        return python_path_rows(*self._level_axes(samp_level), self.x_cl)
+
+    def _prepare_level(self, samp_level: int, as_matrix: bool = False):
+        """Host work of one sampling level: the three axes (or, for the multi-agent batch, the expanded matrix) and the
+        time tables of its durations.  A level is ALWAYS a cartesian product, so the single-planner path hands the device
+        the axes (frx_plan_grid, ~1 kB over PCIe) and never builds the [N, 13] matrix on the host."""
+        axes = self._level_axes(samp_level)
+        self._total_count = axes[0].size * axes[1].size * axes[2].size
         self._bundle = None                      # device buffers are recycled by the next plan
-        self.handler.set_time_tables(*hotpath.time_tables(hotpath.distinct_durations(sampling), self.dT, self.N + 1))
-        return sampling
+        self.handler.set_time_tables(*hotpath.time_tables(np.unique(axes[0]), self.dT, self.N + 1))
+        return python_path_rows(*axes, self.x_cl) if as_matrix else axes
 
-    def _make_bundle(self, sampling: np.ndarray) -> TrajectoryBundle:
-        self._bundle = TrajectoryBundle(self.handler, sampling.shape[0], self.cost_names, self.cost_weight_list, self.dT,
-                                        self.horizon, self.N + 1, self._LOW_VEL_MODE, sampling=sampling)
+    def _make_bundle(self, sampling=None, axes=None) -> TrajectoryBundle:
+        n = sampling.shape[0] if sampling is not None else axes[0].size * axes[1].size * axes[2].size
+        self._bundle = TrajectoryBundle(self.handler, n, self.cost_names, self.cost_weight_list, self.dT,
+                                        self.horizon, self.N + 1, self._LOW_VEL_MODE, sampling=sampling,
+                                        grid=None if axes is None else (*axes, self.x_cl))
         return self._bundle
 
     def plan(self) -> tuple:
@@ -347,9 +358,9 @@ class ReactivePlannerB200:
         self._push_static_inputs()
         samp_level = self._sampling_min
         while optimal_trajectory is None and samp_level < self._sampling_max:
-            sampling = self._prepare_level(samp_level)
-            res = hotpath.PlanOutput.from_result(self.handler.plan(sampling))
-            optimal_trajectory = self._get_optimal_trajectory(self._make_bundle(sampling), res, samp_level)
+            axes = self._prepare_level(samp_level)
+            res = hotpath.PlanOutput.from_result(self.handler.plan_grid(*axes, self.x_cl))
+            optimal_trajectory = self._get_optimal_trajectory(self._make_bundle(axes=axes), res, samp_level)
             samp_level += 1
         return self._finish_plan(optimal_trajectory, time.time() - t0)
 
@@ -379,23 +390,42 @@ class ReactivePlannerB200:
         self.infeasible_kinematics_percentage = float(res.n_feasible / res.n_in_list) * 100 if res.n_in_list else 0.0
         self.last_plan_stats = res
         if self._draw_traj_set or self.save_all_traj:
-            bundle.sort()
+            bundle.sort()                        # reads flags + costs of every row to the host: they outlive the next plan
             self.all_traj = bundle.trajectories
         if res.argmin >= 0:
-            return bundle.sample(res.argmin)
+            return bundle.sample(res.argmin - bundle.row_base).detach()
         if samp_lvl >= self._sampling_max - 1 and res.n_feasible > 0:
-            # reference: lowest ego_risk + obst_risk among the feasible ones (needs risk_assessment, host side);
-            # a user-supplied risk function keeps that behaviour, otherwise the cheapest feasible one is taken
-            fl = bundle.flags
-            feas = np.flatnonzero(((fl & _capi.FLAG_VALID) != 0) & ((fl & _capi.FLAG_FEASIBLE) != 0) &
-                                  ((fl & _capi.FLAG_IN_LIST) != 0))
-            risk_fn = getattr(self, "risk_function", None)
-            self.msg_logger.warning("No optimal trajectory available. Select lowest risk trajectory!")
-            if risk_fn is not None:
-                risks = np.array([risk_fn(bundle.sample(int(r))) for r in feas])
-                return bundle.sample(int(feas[np.argmin(risks)]))
-            return bundle.sample(int(feas[np.argmin(bundle.total[feas])]))
+            return self._select_min_risk(bundle)
         return None
+
+    def _select_min_risk(self, bundle: TrajectoryBundle):
+        """reactive_planner.py:262-269: no collision-free candidate at the last level -> the feasible trajectory with the
+        lowest ``ego_risk + obst_risk``.  The risk model (risk_assessment.calc_risk: harm x collision probability) lives
+        on the host in the reference; a ``risk_function(sample) -> float`` attribute plugs it in unchanged.  Without one
+        the device results give a proxy in the same spirit -- every remaining candidate collides or leaves the road, so
+        prefer (1) staying on the road, (2) the LATEST first collision, (3) the lowest prediction cost (inverse
+        Mahalanobis proximity to the predicted obstacles), (4) the total cost -- and say loudly that this is not the
+        reference's risk."""
+        fl = bundle.flags
+        feas = np.flatnonzero(((fl & _capi.FLAG_VALID) != 0) & ((fl & _capi.FLAG_FEASIBLE) != 0) &
+                              ((fl & _capi.FLAG_IN_LIST) != 0))
+        if feas.size == 0:
+            return None
+        self.msg_logger.warning("No optimal trajectory available. Select lowest risk trajectory!")
+        risk_fn = getattr(self, "risk_function", None)
+        if risk_fn is not None:
+            risks = np.array([risk_fn(bundle.sample(int(r))) for r in feas])
+            return bundle.sample(int(feas[np.argmin(risks)])).detach()
+        self.msg_logger.warning("risk_assessment is not attached (planner.risk_function): ranking by road departure, time "
+                                "of first collision, prediction cost and total cost instead of ego_risk + obst_risk")
+        f = fl[feas]
+        off_road = (f & _capi.FLAG_BOUNDARY) != 0
+        hit = (f & _capi.FLAG_COLLIDE) != 0
+        first_hit = np.where(hit, (f >> _capi.FLAG_COLLIDE_STEP_SHIFT) & 63, 64).astype(np.int64)
+        pred = bundle.costs[feas, self.cost_names.index("prediction")] if "prediction" in self.cost_names \
+            else np.zeros(feas.size)
+        order = np.lexsort((feas, bundle.total[feas], pred, -first_hit, off_road))     # last key is the primary one
+        return bundle.sample(int(feas[order[0]])).detach()
 
     # ------------------------------------------------------------------------------------------
     # output conversion (planner.py:394-515) without commonroad-io
@@ -496,12 +526,12 @@ def plan_batched(planners: List["ReactivePlannerB200"]) -> list:
     for p in planners:
         optimal[id(p)] = None
     while pending:
-        mats = [p._prepare_level(level[id(p)]) for p in pending]
+        mats = [p._prepare_level(level[id(p)], as_matrix=True) for p in pending]
         results = _capi.plan_batched([p.handler for p in pending], mats)
         nxt = []
         for p, S, r in zip(pending, mats, results):
             res = hotpath.PlanOutput.from_result(r)
-            opt = p._get_optimal_trajectory(p._make_bundle(S), res, level[id(p)])
+            opt = p._get_optimal_trajectory(p._make_bundle(sampling=S), res, level[id(p)])
             level[id(p)] += 1
             optimal[id(p)] = opt
             if opt is None and level[id(p)] < p._sampling_max:

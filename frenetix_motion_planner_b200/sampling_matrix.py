@@ -11,7 +11,6 @@ level so that large grids can be expanded on the GPU (``frx_plan_grid``) instead
 """
 from __future__ import annotations
 
-import itertools
 from typing import Iterable, Sequence
 
 import numpy as np
@@ -120,21 +119,35 @@ def generate_sampling_matrix(*, t0_range, t1_range, s0_range, ss0_range, sss0_ra
 def python_path_rows(t_set: Iterable[float], v_set: Iterable[float], d_set: Iterable[float], x_cl) -> np.ndarray:
     """Rows in the generation order of the reference's Python path (reactive_planner.py:149-175):
     ``for t: for v: for d`` over the *sets* in their native iteration order, so that the row index
-    equals the reference's ``uniqueId``."""
+    equals the reference's ``uniqueId``.  Vectorised: one repeat / tile per axis, no Python loop over rows."""
     (s0, ss0, sss0), (d0, dd0, ddd0) = x_cl
-    rows = [(0.0, t, s0, ss0, sss0, v, 0.0, d0, dd0, ddd0, d, 0.0, 0.0)
-            for t, v, d in itertools.product(t_set, v_set, d_set)]
-    return np.array(rows, dtype=np.float64).reshape(-1, 13)
+    t = np.fromiter(t_set, dtype=np.float64)
+    v = np.fromiter(v_set, dtype=np.float64)
+    d = np.fromiter(d_set, dtype=np.float64)
+    n = t.size * v.size * d.size
+    S = np.zeros((n, 13), dtype=np.float64)
+    S[:, 1] = np.repeat(t, v.size * d.size)
+    S[:, 2], S[:, 3], S[:, 4] = s0, ss0, sss0
+    S[:, 5] = np.tile(np.repeat(v, d.size), t.size)
+    S[:, 7], S[:, 8], S[:, 9] = d0, dd0, ddd0
+    S[:, 10] = np.tile(d, t.size * v.size)
+    return S
 
 
 def sampling_axes(handler: SamplingHandler, level: int, x_cl, cpp_style: bool = False):
-    """The three axes of sampling level `level`.  ``cpp_style`` adds the extra members the C++ path
-    unions in (reactive_planner_cpp.py:235-237: t ∪ {N·dT}, v ∪ {ss0}); the Python path only adds d0."""
+    """The three axes of sampling level `level`, as the very set objects the reference iterates.
+
+    Iteration order of a Python set depends on its hash-table size, and a *copy* of a set can land in a different table
+    size than the original -- so the sets are handed out exactly as the reference builds them: the Python path iterates
+    ``t_sampling.to_range(level)`` and ``v_sampling.to_range(level)`` themselves and one ``.union({d0})`` copy of the d
+    set (reactive_planner.py:149-158); the C++ path takes one ``.union`` of each (reactive_planner_cpp.py:235-237:
+    t with {N*dT}, v with {ss0}, d with {d0}).  Row index == the reference's ``uniqueId`` depends on it."""
     (s0, ss0, sss0), (d0, dd0, ddd0) = x_cl
-    t_set = set(handler.t_sampling.to_range(level))
-    v_set = set(handler.v_sampling.to_range(level))
-    d_set = set(handler.d_sampling.to_range(level)).union({d0})
     if cpp_style:
-        t_set = t_set.union({round(handler.horizon / handler.dt) * handler.dt})
-        v_set = v_set.union({ss0})
+        t_set = handler.t_sampling.to_range(level).union({round(handler.horizon / handler.dt) * handler.dt})
+        v_set = handler.v_sampling.to_range(level).union({ss0})
+    else:
+        t_set = handler.t_sampling.to_range(level)
+        v_set = handler.v_sampling.to_range(level)
+    d_set = handler.d_sampling.to_range(level).union({d0})
     return t_set, v_set, d_set

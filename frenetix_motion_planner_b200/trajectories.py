@@ -21,6 +21,9 @@ import numpy as np
 
 from . import _capi
 
+_UNSET = object()
+# risk_assessment harm model LR1S "ignore_angle" (configurations/harm_parameters.json: log_reg.ignore_angle)
+DEFAULT_HARM_COEFF = {"const": -4.591, "speed": 0.185}
 _CART = ("x", "y", "theta", "v", "a", "kappa", "kappa_dot")
 _CURV = ("s", "d", "theta", "s_dot", "s_ddot", "d_dot", "d_ddot")   # state fields 7..13
 
@@ -85,23 +88,42 @@ class PolynomialView:
                 720 * c[4] * c[5] * t4 + 720 * c[5] * c[5] * t5)
 
 
+class StaleBundleError(RuntimeError):
+    """A lazy view was asked for data of a plan whose device buffers a later plan has recycled."""
+
+
 class TrajectorySample:
-    """Index proxy of row `row` of a :class:`TrajectoryBundle` (attribute surface: module docstring)."""
+    """Index proxy of row `row` of a :class:`TrajectoryBundle` (attribute surface: module docstring).
+
+    Ownership: in the reference every sample owns its arrays.  Here the arrays stay in HBM until somebody asks, and the
+    next plan on the same handler recycles them.  :meth:`detach` pulls everything the sample can still be asked for to
+    the host (the planner does that for the selected trajectory before it returns it); a sample that was not detached
+    raises :class:`StaleBundleError` instead of silently showing the newer plan's numbers."""
 
     def __init__(self, bundle: "TrajectoryBundle", row: int):
         self._b, self._row = bundle, int(row)
         self.uniqueId = int(row) + bundle.row_base
         self.horizon, self.dt = bundle.horizon, bundle.dt
         self._ego_risk = self._obst_risk = None
-        self.boundary_harm = None
+        self._harm_override = _UNSET
         self.harm_occ_module = None
         self._states = None
         self._coll_override = None
+        self._own = None           # detached copy: (flags, cost, cost row, traj_len, sampling row)
+
+    def detach(self) -> "TrajectorySample":
+        """Make the sample self-contained (host copies of its states and scalars): safe to keep across later plans."""
+        if self._own is None:
+            self._fetch()
+            b, r = self._b, self._row
+            self._own = (int(b.flags[r]), float(b.total[r]), np.array(b.costs[r], dtype=np.float64), int(b.traj_len[r]),
+                         b.sampling_row(r))
+        return self
 
     # ---- scalars --------------------------------------------------------------------------
     @property
     def _flags(self) -> int:
-        return int(self._b.flags[self._row])
+        return self._own[0] if self._own is not None else int(self._b.flags[self._row])
 
     @property
     def feasible(self) -> bool:
@@ -113,16 +135,20 @@ class TrajectorySample:
 
     @property
     def cost(self) -> float:
-        return float(self._b.total[self._row])
+        return self._own[1] if self._own is not None else float(self._b.total[self._row])
+
+    @property
+    def _cost_row(self) -> np.ndarray:
+        return self._own[2] if self._own is not None else self._b.costs[self._row]
 
     @property
     def costMap(self) -> Dict[str, tuple]:
-        c = self._b.costs[self._row]
+        c = self._cost_row
         return {n: (float(c[k]), float(self._b.weights[k] * c[k])) for k, n in enumerate(self._b.cost_names)}
 
     @property
     def cost_list(self) -> list:
-        return [float(v) for v in self._b.costs[self._row]]
+        return [float(v) for v in self._cost_row]
 
     @property
     def _coll_detected(self):
@@ -142,11 +168,36 @@ class TrajectorySample:
 
     @property
     def actual_traj_length(self) -> int:
-        return int(self._b.traj_len[self._row])
+        return self._own[3] if self._own is not None else int(self._b.traj_len[self._row])
 
     @property
     def sampling_parameters(self) -> np.ndarray:
-        return self._b.sampling_row(self._row)
+        return self._own[4] if self._own is not None else self._b.sampling_row(self._row)
+
+    @property
+    def boundary_harm(self):
+        """planner.py:362-381: MAIS3+ probability (logistic regression "ignore_angle", harm_parameters.json) at the velocity
+        of the step where the ego first overlaps the road boundary, 0 when it never does.  A value assigned by a caller
+        (the reference writes the attribute) takes precedence."""
+        if self._harm_override is not _UNSET:
+            return self._harm_override
+        f = self._flags
+        if not f & _capi.FLAG_BOUNDARY:
+            return 0
+        k = (f >> _capi.FLAG_BOUNDARY_STEP_SHIFT) & 63
+        v = float(self._fetch()[3][k])
+        c = self._b.harm_coeff
+        return float(1.0 / (1.0 + np.exp(-c["const"] - c["speed"] * v)))
+
+    @boundary_harm.setter
+    def boundary_harm(self, value):
+        self._harm_override = value
+
+    @property
+    def first_collision_step(self) -> int:
+        """Index of the first ego hull that meets a predicted obstacle (time index t0 + k), -1 when there is none."""
+        f = self._flags
+        return int((f >> _capi.FLAG_COLLIDE_STEP_SHIFT) & 63) if f & _capi.FLAG_COLLIDE else -1
 
     # ---- polynomials ----------------------------------------------------------------------
     @property
@@ -232,14 +283,23 @@ class TrajectoryBundle:
         self._cache: Dict[int, TrajectorySample] = {}
         self._is_sorted = False
         self.winner_row: Optional[int] = None     # local row of the last plan's arg-min (set by the planner)
+        self._gen = getattr(handler, "generation", 0)     # the plan these views belong to
+        self.harm_coeff = dict(DEFAULT_HARM_COEFF)
+
+    def _live(self):
+        if getattr(self._h, "generation", self._gen) != self._gen:
+            raise StaleBundleError("this TrajectoryBundle belongs to an earlier plan: the handler has planned again and "
+                                   "recycled the device buffers (read what you need, or detach() samples, before the next plan())")
 
     # ---- bulk, lazily read back ------------------------------------------------------------
     def _read_flags(self):
         if self._flags is None:
+            self._live()
             self._flags, self._traj_len = self._h.get_flags(0, self.n_rows)
 
     def _read_costs(self):
         if self._total is None:
+            self._live()
             self._costs, self._total = self._h.get_costs(0, self.n_rows)
 
     @property
@@ -263,6 +323,7 @@ class TrajectoryBundle:
         return self._total
 
     def states_of(self, row: int) -> np.ndarray:
+        self._live()
         if self.winner_row is not None and int(row) == self.winner_row:
             # the selected candidate's rows came back with the arg-min (mapped result record): no device round trip
             return self._h.winner_states()
@@ -270,6 +331,7 @@ class TrajectoryBundle:
 
     def states(self, rows, fields=None) -> np.ndarray:
         """[n_fields, len(rows), Nt] gather for many rows at once (logging / visualisation)."""
+        self._live()
         return self._h.get_states(np.asarray(rows, dtype=np.int64), fields)
 
     def sampling_row(self, row: int) -> np.ndarray:

@@ -101,6 +101,10 @@ class Params:
         "distance_to_reference_path": 5.0, "prediction": 0.2})
     # distance_to_obstacles needs the obstacles' current positions [[x, y], ...]
     obstacle_positions: Optional[np.ndarray] = None
+    # the `s_velocity > 0.001` stand-still threshold of reactive_planner.py:393-447.  Tests move it by +-1e-9 to get BOTH
+    # outcomes of a candidate whose velocity profile is constructed to end at exactly 0.001 m/s (a structural tie that
+    # LAPACK rounding noise decides in the reference itself): the device must reproduce one of the two.
+    standstill_threshold: float = 0.001
 
     def active_costs(self):
         names = [k for k, w in self.cost_weights.items() if w != 0]
@@ -462,12 +466,12 @@ def check_feasibility_one(row, ref: RefPath, prm: Params):
         for i in range(0, Nt):
             if not prm.low_vel_mode:
                 upd(s_velocity[i] - 0.001)
-                if s_velocity[i] > 0.001:
+                if s_velocity[i] > prm.standstill_threshold:
                     dp = d_velocity[i] / s_velocity[i]
                 else:
                     dp = 0.
                 ddot = d_acceleration[i] - dp * s_acceleration[i]
-                if s_velocity[i] > 0.001:
+                if s_velocity[i] > prm.standstill_threshold:
                     dpp = ddot / (s_velocity[i] ** 2)
                 else:
                     dpp = 0.
@@ -482,7 +486,7 @@ def check_feasibility_one(row, ref: RefPath, prm: Params):
                 break
             s_lambda = (s[i] - ref_pos[s_idx]) / (ref_pos[s_idx + 1] - ref_pos[s_idx])
 
-            if s_velocity[i] > 0.001 or prm.low_vel_mode:
+            if s_velocity[i] > prm.standstill_threshold or prm.low_vel_mode:
                 theta_cl[i] = np.arctan2(dp, 1.0)
                 theta_gl[i] = theta_cl[i] + interpolate_angle(
                     s[i], ref_pos[s_idx], ref_pos[s_idx + 1], ref_theta[s_idx], ref_theta[s_idx + 1])

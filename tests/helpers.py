@@ -97,10 +97,45 @@ def device_plan(sampling, ref, prm, preds, static_obbs=None, device=0, handler=N
 BAND = 1e-9   # decision margin below which the reference's own outcome is rounding noise
 
 
-def compare_with_oracle(dev, ora, prm, tol=1e-6, check_collide=True, band=BAND):
+def band_alternatives(sampling, ref, prm, preds, rows, static_obbs=None):
+    """Both legal outcomes of the candidates `rows` that sit on the `s_velocity > 0.001` tie (oracle docstring): the
+    oracle with the stand-still threshold moved just below and just above 0.001."""
+    import dataclasses
+    rows = np.asarray(rows, dtype=np.int64)
+    outs = []
+    for thr in (0.001 - 2e-9, 0.001 + 2e-9):
+        outs.append(fo.plan(np.asarray(sampling)[rows], ref, dataclasses.replace(prm, standstill_threshold=thr), preds,
+                            static_obbs=static_obbs))
+    return rows, outs
+
+
+def assert_band_rows_take_a_legal_branch(dev, alts, bits, tol):
+    """Every in-band candidate must equal the oracle on ONE side of the tie: same mask bits, states / costs within `tol`."""
+    rows, outs = alts
+    for j, r in enumerate(rows):
+        ok_any = False
+        why = []
+        for o in outs:
+            if (int(dev["flags"][r]) ^ int(o["flags"][j])) & bits:
+                why.append(f"flags {int(dev['flags'][r]) & bits:#x} vs {int(o['flags'][j]) & bits:#x}")
+                continue
+            e = 0.0
+            if dev["states"] is not None and (int(o["flags"][j]) & fo.FLAG_STORED):
+                e = max(e, rel_err(dev["states"][:, r, :], o["states"][:, j, :]))
+            if int(o["flags"][j]) & fo.FLAG_COSTED:
+                e = max(e, rel_err(dev["costs"][r], o["costs"][j]), rel_err(dev["total"][r], o["total"][j]))
+            if e < tol and dev["traj_len"][r] == o["traj_len"][j]:
+                ok_any = True
+                break
+            why.append(f"rel err {e:.2e}")
+        assert ok_any, f"in-band row {r} matches neither side of the stand-still tie: {why}"
+
+
+def compare_with_oracle(dev, ora, prm, tol=1e-6, check_collide=True, band=BAND, alts=None):
     """Assert the parity contract: masks / selected index bit-exact, states & costs within `tol`
-    relative -- for every candidate whose decision margins exceed `band`; the rest
-    sit on structural ties of the reference (see oracle docstring) and are only counted."""
+    relative -- for every candidate whose decision margins exceed `band`.  The rest
+    sit on a structural tie of the reference (see oracle docstring): with `alts` (band_alternatives) each of them
+    must equal the oracle on one of the two sides of the tie; without, they are only counted."""
     from oracle import frenet_oracle as fo
     ok = ora["margins"] >= band if "margins" in ora else np.ones(len(ora["flags"]), bool)
     n_band = int((~ok).sum())
@@ -110,6 +145,9 @@ def compare_with_oracle(dev, ora, prm, tol=1e-6, check_collide=True, band=BAND):
         bits |= fo.reason_bit(r)
     if check_collide:
         bits |= fo.FLAG_COLLIDE | fo.FLAG_BOUNDARY
+    if alts is not None:
+        assert set(alts[0].tolist()) == set(np.flatnonzero(~ok).tolist()), "alternatives must cover exactly the in-band rows"
+        assert_band_rows_take_a_legal_branch(dev, alts, bits, tol)
     diff = ((fl_d ^ fl_o) & np.uint64(bits))
     diff[~ok] = 0
     assert not diff.any(), f"{int((diff != 0).sum())} flag mismatches, first rows {np.nonzero(diff)[0][:5]}, " \
