@@ -81,18 +81,44 @@ class CoordinateSystem:
         return np.array([px - d * np.sin(th), py + d * np.cos(th)])
 
     def convert_to_curvilinear_coords(self, x: float, y: float):
-        """(x, y) -> (s, d): closest-segment projection consistent with the definition above
-        (first-order; used only to seed ``x_cl`` in examples and fixtures)."""
-        ref = self._reference
+        """(x, y) -> (s, d): the EXACT inverse of :meth:`convert_to_cartesian_coords` (what pycrccosy's
+        ``convert_to_curvilinear_coords`` is to its own forward map; planner.py:567-571 seeds ``x_cl`` with it).
+
+        On segment i the forward map is P(lam) + d * n(theta(lam)) with a heading that is interpolated along the segment,
+        so the foot point is where the offset vector is perpendicular to the INTERPOLATED tangent:
+        f(lam) = (X - P(lam)) . t(theta(lam)) = 0.  Start from the orthogonal projection onto the closest segment and
+        run Newton on f, stepping into the neighbour segment when lam leaves [0, 1)."""
+        ref, pos, theta = self._reference, self._ref_pos, self._ref_theta
+        X = np.array([x, y], dtype=np.float64)
         a, b = ref[:-1], ref[1:]
         ab = b - a
-        ap = np.array([x, y]) - a
-        lam = np.clip(np.sum(ap * ab, axis=1) / np.sum(ab * ab, axis=1), 0.0, 1.0)
-        q = a + lam[:, None] * ab
-        dist2 = np.sum((np.array([x, y]) - q) ** 2, axis=1)
-        i = int(np.argmin(dist2))
-        s = self._ref_pos[i] + lam[i] * (self._ref_pos[i + 1] - self._ref_pos[i])
-        th = self._ref_theta[i] + lam[i] * (self._ref_theta[i + 1] - self._ref_theta[i])
+        lam0 = np.clip(np.sum((X - a) * ab, axis=1) / np.sum(ab * ab, axis=1), 0.0, 1.0)
+        q = a + lam0[:, None] * ab
+        i = int(np.argmin(np.sum((X - q) ** 2, axis=1)))
+        lam = float(lam0[i])
+        n_seg = ref.shape[0] - 1
+        for _ in range(50):
+            th = theta[i] + lam * (theta[i + 1] - theta[i])
+            t = np.array([np.cos(th), np.sin(th)])
+            n = np.array([-np.sin(th), np.cos(th)])
+            r = X - (a[i] + lam * ab[i])
+            f = float(np.dot(r, t))
+            df = -float(np.dot(ab[i], t)) + float(np.dot(r, n)) * (theta[i + 1] - theta[i])
+            step = f / df if df != 0.0 else 0.0
+            lam_new = lam - step
+            if lam_new < 0.0 and i > 0:
+                i, lam = i - 1, 1.0 - 1e-12     # continue at the end of the previous segment
+                continue
+            if lam_new >= 1.0 and i < n_seg - 1:
+                i, lam = i + 1, 0.0
+                continue
+            lam_new = min(max(lam_new, 0.0), 1.0)
+            if abs(lam_new - lam) <= 1e-15:
+                lam = lam_new
+                break
+            lam = lam_new
+        th = theta[i] + lam * (theta[i + 1] - theta[i])
         n = np.array([-np.sin(th), np.cos(th)])
-        d = float(np.dot(np.array([x, y]) - q[i], n))
+        s = pos[i] + lam * (pos[i + 1] - pos[i])
+        d = float(np.dot(X - (a[i] + lam * ab[i]), n))
         return np.array([s, d])

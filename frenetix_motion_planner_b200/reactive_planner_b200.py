@@ -61,13 +61,13 @@ class _Trajectory(SimpleNamespace):
 
 class ReactivePlannerB200:
     def __init__(self, config_plan, config_sim, scenario=None, planning_problem=None, log_path=None, work_dir=None,
-                 msg_logger=None, device: int = 0):
+                 msg_logger=None, device: int = 0, handler=None):
         self.config_plan, self.config_sim = config_plan, config_sim
         planning, debug = _get(config_plan, "planning"), _get(config_plan, "debug")
         self.horizon = _get(planning, "planning_horizon")
         self.dT = _get(planning, "dt")
         self.N = int(self.horizon / self.dT)
-        assert self.dT > 0 and self.N > 0 and self.horizon > 0
+        self._check_valid_settings()
         self.vehicle_params = _get(config_sim, "vehicle")
         self._low_vel_mode_threshold = _get(planning, "low_vel_mode_threshold", 2.0)
         self.msg_logger = msg_logger or logging.getLogger("Message_logger")
@@ -91,6 +91,9 @@ class ReactivePlannerB200:
         self.use_prediction = False
         self._collision_counter = 0
         self._total_count = 0
+        self._infeasible_count_collision = 0
+        self._optimal_cost = 0
+        self.max_seen_costs = 1
         self._infeasible_count_kinematics = None
         self.infeasible_kinematics_percentage = None
         self._sampling_min = _get(planning, "sampling_min", 2)
@@ -116,10 +119,17 @@ class ReactivePlannerB200:
 
         self.cost_weights = dict(_get(_get(config_plan, "cost"), "cost_weights", {}) or {})
         self.set_cost_function(self.cost_weights)
+        # risk / harm parameters (planner.py:156-159 loads configurations/{harm_parameters,risk}.json): only the LR1S
+        # "ignore_angle" coefficients reach the hot path (boundary_harm, planner.py:370-381)
+        from .trajectories import DEFAULT_HARM_COEFF
+        self.params_harm = {"log_reg": {"ignore_angle": dict(DEFAULT_HARM_COEFF)}}
+        self.params_risk = None
 
-        # ---- device side: fails loudly if libfrx_b200.so or the GPU is missing (no CPU fallback)
-        self.handler = _capi.Handler(device)
+        # ---- device side: fails loudly if libfrx_b200.so or the GPU is missing (no CPU fallback).  `handler` lets a caller
+        # share an existing context (and the drop-in tests substitute their recorder); nothing in the package passes it.
+        self.handler = handler if handler is not None else _capi.Handler(device)
         self._bundle: Optional[TrajectoryBundle] = None
+        self._prefetched = None                 # (input signature, optimal trajectory) left by prefetch_plans()
         self._ref_dirty = True
         self._pred_dirty = True
         self.last_plan_stats = None
@@ -351,16 +361,43 @@ class ReactivePlannerB200:
                                         grid=None if axes is None else (*axes, self.x_cl))
         return self._bundle
 
+    def _create_trajectory_bundle(self, x_0_lon=None, x_0_lat=None, cost_function=None, samp_level: int = None) -> TrajectoryBundle:
+        """reactive_planner.py:132-182.  The reference builds one TrajectorySample object per (t, v, d) here and evaluates
+        them later; on the device sampling, feasibility, costs, collision sweep and arg-min are ONE launch, so the bundle
+        that comes back is already evaluated (``bundle.result`` holds the plan's summary record)."""
+        if x_0_lon is not None and x_0_lat is not None:
+            self.x_cl = (list(x_0_lon), list(x_0_lat))
+        if cost_function is not None and cost_function is not self.cost_function:
+            self.set_cost_function(cost_function)
+        axes = self._prepare_level(samp_level)
+        res = hotpath.PlanOutput.from_result(self.handler.plan_grid(*axes, self.x_cl))
+        bundle = self._make_bundle(axes=axes)
+        bundle.result = res
+        return bundle
+
+    def _input_signature(self):
+        """Everything a plan depends on that changes between simulation steps: a prefetched plan is only used by the
+        plan() call that sees the very same inputs (and no other plan on this handler in between)."""
+        x = self.x_0
+        pos = getattr(x, "position", None)
+        return (None if pos is None else (float(pos[0]), float(pos[1])), float(x.orientation), float(x.velocity),
+                getattr(x, "time_step", None), tuple(float(v) for v in self.x_cl[0]), tuple(float(v) for v in self.x_cl[1]),
+                None if self.desired_velocity is None else float(self.desired_velocity), id(self.predictions),
+                id(self.coordinate_system), self.handler.generation)
+
     def plan(self) -> tuple:
         """reactive_planner.py:67-130 with the per-candidate work on the device."""
         optimal_trajectory = None
         t0 = time.time()
+        pre, self._prefetched = self._prefetched, None
+        if pre is not None and pre[0] == self._input_signature():
+            # the multi-agent batch already evaluated this very plan in its one launch (prefetch_plans)
+            return self._finish_plan(pre[1], time.time() - t0)
         self._push_static_inputs()
         samp_level = self._sampling_min
         while optimal_trajectory is None and samp_level < self._sampling_max:
-            axes = self._prepare_level(samp_level)
-            res = hotpath.PlanOutput.from_result(self.handler.plan_grid(*axes, self.x_cl))
-            optimal_trajectory = self._get_optimal_trajectory(self._make_bundle(axes=axes), res, samp_level)
+            bundle = self._create_trajectory_bundle(self.x_cl[0], self.x_cl[1], self.cost_function, samp_level=samp_level)
+            optimal_trajectory = self._get_optimal_trajectory(bundle, samp_level)
             samp_level += 1
         return self._finish_plan(optimal_trajectory, time.time() - t0)
 
@@ -376,9 +413,10 @@ class ReactivePlannerB200:
         self.plan_postprocessing(optimal_trajectory=optimal_trajectory, planning_time=planning_time)
         return self.trajectory_pair
 
-    def _get_optimal_trajectory(self, bundle: TrajectoryBundle, res, samp_lvl):
+    def _get_optimal_trajectory(self, bundle: TrajectoryBundle, samp_lvl, res=None):
         """reactive_planner.py:184-272: statistics, all_traj, selection (device arg-min == first collision-free
         entry of the cost-sorted feasible list)."""
+        res = res if res is not None else bundle.result
         self._collision_counter = res.collision_counter
         if res.argmin is not None and int(res.argmin) >= 0:
             bundle.winner_row = int(res.argmin) - bundle.row_base
@@ -486,6 +524,101 @@ class ReactivePlannerB200:
                                _ego_risk=None, _obst_risk=None, boundary_harm=None, _coll_detected=None,
                                actual_traj_length=N)
 
+    # ------------------------------------------------------------------------------------------
+    # the remaining members of the reference classes (planner.py / reactive_planner.py), device-backed
+    # ------------------------------------------------------------------------------------------
+    def _check_valid_settings(self):
+        """planner.py:544-548"""
+        assert self.dT > 0, 'provided dt is not correct! dt = {}'.format(self.dT)
+        assert self.N > 0 and isinstance(self.N, int), 'N is not correct!'
+        assert self.horizon > 0, 'provided t_h is not correct! dt = {}'.format(self.horizon)
+
+    def set_stopping_point(self, stop_s_coordinate):
+        self.stopping_s = stop_s_coordinate                   # planner.py:664-669
+
+    def shift_orientation(self, trajectory, interval_start=-np.pi, interval_end=np.pi):
+        """planner.py:536-542"""
+        for state in trajectory.state_list:
+            while state.orientation < interval_start:
+                state.orientation += 2 * np.pi
+            while state.orientation > interval_end:
+                state.orientation -= 2 * np.pi
+        return trajectory
+
+    def _compute_cart_traj(self, trajectory):
+        """planner.py:449-486: the Cartesian state list of a sample (yaw rate by np.gradient, no orientation shift)."""
+        c = trajectory.cartesian
+        t0 = getattr(self.x_0, "time_step", 0)
+        yaw = np.gradient(np.asarray(c.theta)) / self.dT
+        yaw[0] = getattr(self.x_0, "yaw_rate", 0.0)
+        steer = np.arctan2(_get(self.vehicle_params, "wheelbase") * np.asarray(c.kappa), 1.0)
+        return _Trajectory(initial_time_step=t0, state_list=[
+            PlannerState(time_step=int(t0 + i), position=np.array([c.x[i], c.y[i]]), orientation=c.theta[i], velocity=c.v[i],
+                         acceleration=c.a[i], yaw_rate=yaw[i], steering_angle=steer[i]) for i in range(len(c.x))])
+
+    def create_coll_object(self, trajectory, vehicle_params=None, ego_state=None):
+        """planner.py:517-534 builds a pycrcc time-variant obstacle of obb-sum hulls.  pycrcc is not a dependency of this
+        package; what it would hold is returned as an array: one row per hull k = (cx, cy, theta, half_len, half_wid), the
+        box in the frame of box k that contains the ego boxes k and k + 1 -- the same hulls the
+        kernels test.  `trajectory`: the object convert_state_list_to_commonroad_object returns."""
+        vp = vehicle_params or self.vehicle_params
+        hl, hw = _get(vp, "length") / 2, _get(vp, "width") / 2
+        st = trajectory.prediction.trajectory.state_list
+        rows = []
+        for a, b in zip(st[:-1], st[1:]):
+            ux, uy = math.cos(a.orientation), math.sin(a.orientation)
+            dx, dy = b.position[0] - a.position[0], b.position[1] - a.position[1]
+            du, dv = dx * ux + dy * uy, dy * ux - dx * uy
+            c = abs(ux * math.cos(b.orientation) + uy * math.sin(b.orientation))
+            sn = abs(ux * math.sin(b.orientation) - uy * math.cos(b.orientation))
+            eu, ev = hl * c + hw * sn, hl * sn + hw * c
+            lo_u, hi_u, lo_v, hi_v = min(-hl, du - eu), max(hl, du + eu), min(-hw, dv - ev), max(hw, dv + ev)
+            mu, mv = 0.5 * (lo_u + hi_u), 0.5 * (lo_v + hi_v)
+            rows.append([a.position[0] + mu * ux - mv * uy, a.position[1] + mu * uy + mv * ux, a.orientation,
+                         0.5 * (hi_u - lo_u), 0.5 * (hi_v - lo_v)])
+        return np.array(rows)
+
+    def check_feasibility(self, trajectories, queue_1=None, queue_2=None):
+        """reactive_planner.py:274-577 evaluates the kinematics of a list of samples.  Samples of a device bundle arrive
+        evaluated (``feasible`` / ``valid`` / the state arrays are read from the plan's result), so this only hands the
+        list back -- through the queues when the caller passed them, like the multiprocessing variant (:207-224)."""
+        trajectory_list = list(trajectories)
+        if queue_1 is not None:
+            queue_1.put(trajectory_list)
+            if self._kinematic_debug and queue_2 is not None:
+                queue_2.put(list(self._infeasible_count_kinematics or [0] * 11))
+            return None
+        return trajectory_list
+
+    def trajectory_collision_check(self, feasible_trajectories):
+        """planner.py:329-392 on the device's per-candidate verdicts: walk the (cost-sorted) list, count the candidates
+        that meet a predicted obstacle, return the first one that neither collides nor leaves the road.  plan() does not
+        call this -- the arg-min kernel already returns that candidate -- it serves callers that walk a list themselves."""
+        for trajectory in feasible_trajectories:
+            if self.use_occ_model and trajectory.valid is False:
+                continue
+            collision_detected = bool(trajectory._coll_detected) if self.use_prediction else False
+            if collision_detected:
+                self._collision_counter += 1
+            boundary_harm = trajectory.boundary_harm
+            trajectory.boundary_harm = boundary_harm
+            trajectory._coll_detected = collision_detected
+            if not collision_detected and boundary_harm == 0:
+                return trajectory
+        return None
+
+    def set_risk_costs(self, trajectory):
+        """planner.py:312-327 (risk_assessment.calc_risk, host side in the reference, out of scope here): with a
+        ``risk_function(sample) -> float`` attached its value is booked as the ego risk; otherwise the device-side proxies
+        are -- boundary harm for the ego, the inverse-Mahalanobis prediction cost for the obstacles."""
+        risk_fn = getattr(self, "risk_function", None)
+        if risk_fn is not None:
+            trajectory._ego_risk, trajectory._obst_risk = float(risk_fn(trajectory)), 0.0
+        else:
+            pred = trajectory.costMap.get("prediction", (0.0, 0.0))[0] if hasattr(trajectory, "costMap") else 0.0
+            trajectory._ego_risk, trajectory._obst_risk = float(trajectory.boundary_harm or 0.0), float(pred)
+        return trajectory
+
     def plan_postprocessing(self, optimal_trajectory, planning_time, replanning_counter=0):
         """planner.py:637-649: hand the result to the reference's logger when one is attached."""
         if optimal_trajectory is not None and self.logger:
@@ -508,34 +641,41 @@ def hotpath_make_valid_orientation(angle: float) -> float:
     return angle
 
 
-def plan_batched(planners: List["ReactivePlannerB200"]) -> list:
+def prefetch_plans(planners: List["ReactivePlannerB200"]) -> None:
     """All agents of a multi-agent step in ONE eval-kernel launch per sampling level.
 
     The reference steps its agents one after the other (cr_scenario_handler/simulation/agent_batch.py:186-189 ->
-    agent.py:236 -> planner.plan()).  Here every planner does its host-side preparation, then the sampling
-    matrices of all of them go through ``frx_plan_batched`` together, then every planner finishes its own
-    plan() (statistics, selection, output conversion).  Planners that found nothing re-enter the next round
-    with their next sampling level, exactly like the while-loop of reactive_planner.py:84-97.
-    Returns the trajectory pairs in the order of `planners`."""
-    t0 = time.time()
+    agent.py:230-236 -> planner_interface.update_planner / step_interface -> planner.plan()).  Call this between the
+    agents' ``update_planner`` and their ``step_interface``: every planner does its host-side preparation, the sampling
+    levels of all of them go through ``frx_plan_batched`` together (planners that found nothing re-enter the next round
+    with their next level, exactly like the while-loop of reactive_planner.py:84-97), and each planner keeps the
+    outcome.  Its next ``plan()`` -- called by the unmodified ``step_interface`` -- recognises the inputs, skips the
+    device and only does the per-agent tail (output conversion, history, logging).  INTEGRATION.md shows the
+    ``AgentBatch._step_agents`` patch."""
     level, optimal = {}, {}
     for p in planners:
+        p._prefetched = None
         p._push_static_inputs()
         level[id(p)] = p._sampling_min
-    pending = [p for p in planners if level[id(p)] < p._sampling_max]
-    for p in planners:
         optimal[id(p)] = None
+    pending = [p for p in planners if level[id(p)] < p._sampling_max]
     while pending:
         mats = [p._prepare_level(level[id(p)], as_matrix=True) for p in pending]
         results = _capi.plan_batched([p.handler for p in pending], mats)
         nxt = []
         for p, S, r in zip(pending, mats, results):
             res = hotpath.PlanOutput.from_result(r)
-            opt = p._get_optimal_trajectory(p._make_bundle(sampling=S), res, level[id(p)])
+            opt = p._get_optimal_trajectory(p._make_bundle(sampling=S), level[id(p)], res)
             level[id(p)] += 1
             optimal[id(p)] = opt
             if opt is None and level[id(p)] < p._sampling_max:
                 nxt.append(p)
         pending = nxt
-    dt = time.time() - t0
-    return [p._finish_plan(optimal[id(p)], dt) for p in planners]
+    for p in planners:
+        p._prefetched = (p._input_signature(), optimal[id(p)])
+
+
+def plan_batched(planners: List["ReactivePlannerB200"]) -> list:
+    """prefetch_plans + every planner's own plan(): the trajectory pairs in the order of `planners`."""
+    prefetch_plans(planners)
+    return [p.plan() for p in planners]

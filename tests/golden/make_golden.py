@@ -225,20 +225,127 @@ def inactive_cost_case():
     print("inactive costs ok")
 
 
+def sampling_order_cases():
+    """Iteration order of the reference's level SETS (python hash order: it fixes uniqueId = row index and every
+    equal-cost tie) for random v / d intervals, all levels, plus the cpp path's unions -> ref_sampling_order.npz."""
+    rng = np.random.default_rng(99)
+    out = {}
+    cases = []
+    for k in range(24):
+        v_lo = float(np.round(rng.uniform(0.001, 8.0), int(rng.integers(1, 6))))
+        v_hi = v_lo + float(np.round(rng.uniform(0.5, 20.0), int(rng.integers(1, 6))))
+        d_half = float(rng.choice([3.0, 2.5, 1.75, 4.0]))
+        t_min = float(rng.choice([1.1, 0.9, 0.5]))
+        horizon = float(rng.choice([3.0, 5.0]))
+        sh = SamplingHandler(dt=0.1, max_sampling_number=4, t_min=t_min, horizon=horizon, delta_d_max=d_half,
+                             delta_d_min=-d_half, d_ego_pos=False)
+        sh.set_v_sampling(v_lo, v_hi)
+        d0, ss0 = float(rng.uniform(-1, 1)), float(rng.uniform(v_lo, v_hi))
+        cases.append([v_lo, v_hi, d_half, t_min, horizon, d0, ss0])
+        for lvl in range(4):
+            # reactive_planner.py:149-158: the python path iterates these very objects
+            out[f"c{k}_l{lvl}_t"] = np.array(list(sh.t_sampling.to_range(lvl)))
+            out[f"c{k}_l{lvl}_v"] = np.array(list(sh.v_sampling.to_range(lvl)))
+            out[f"c{k}_l{lvl}_d"] = np.array(list(sh.d_sampling.to_range(lvl).union({d0})))
+            # reactive_planner_cpp.py:235-237
+            N = int(horizon / 0.1)
+            out[f"c{k}_l{lvl}_t_cpp"] = np.array(list(sh.t_sampling.to_range(lvl).union({N * 0.1})))
+            out[f"c{k}_l{lvl}_v_cpp"] = np.array(list(sh.v_sampling.to_range(lvl).union({ss0})))
+    out["cases"] = np.array(cases)
+    np.savez_compressed(os.path.join(HERE, "ref_sampling_order.npz"), **out)
+    print("sampling order cases:", len(cases))
+
+
+def independent_projection(cs, X):
+    """(x, y) -> (s, d) WITHOUT the product's inverse: scan the forward map P(s) + d n(s) on a 1 mm raster for the sign
+    change of the tangential miss (X - P(s)) . t(s) next to X, then bisect it.  Stands in for pycrccosy's
+    convert_to_curvilinear_coords (absent), which is the inverse of ITS forward map in the same sense."""
+    poly, pos, theta = np.asarray(cs.reference), cs.ref_pos, cs.ref_theta
+
+    def frame(s):
+        i = int(np.argmax(pos > s)) - 1
+        lam = (s - pos[i]) / (pos[i + 1] - pos[i])
+        P = (1 - lam) * poly[i] + lam * poly[i + 1]
+        th = theta[i] + lam * (theta[i + 1] - theta[i])
+        r = np.asarray(X) - P
+        return r[0] * np.cos(th) + r[1] * np.sin(th), r[1] * np.cos(th) - r[0] * np.sin(th), float(np.hypot(*r))
+    ss = np.arange(pos[0] + 1e-6, pos[-1] - 1e-3, 1e-3)
+    vals = np.array([frame(s) for s in ss])
+    near = vals[:, 2] < vals[:, 2].min() + 0.5
+    k = np.flatnonzero(near[:-1] & (np.sign(vals[:-1, 0]) != np.sign(vals[1:, 0])))
+    assert k.size >= 1, "no foot point found"
+    k = k[np.argmin(vals[k, 2])]
+    lo, hi = ss[k], ss[k + 1]
+    for _ in range(80):
+        mid = 0.5 * (lo + hi)
+        if (frame(mid)[0] > 0) == (frame(lo)[0] > 0):
+            lo = mid
+        else:
+            hi = mid
+    s = 0.5 * (lo + hi)
+    return np.array([s, frame(s)[1]])
+
+
+class _ProjectingCS:
+    """What Planner._compute_initial_states reads from its coordinate system (planner.py:567-635)."""
+
+    def __init__(self, cs):
+        self._cs = cs
+        self.ref_pos, self.ref_theta, self.ref_curv, self.ref_curv_d = cs.ref_pos, cs.ref_theta, cs.ref_curv, cs.ref_curv_d
+
+    def convert_to_curvilinear_coords(self, x, y):
+        return independent_projection(self._cs, (x, y))
+
+
+def reference_initial_state(cs, x_0, low_vel_mode):
+    """The reference's OWN Planner._compute_initial_states (unmodified, planner.py:567-635) on a fake self."""
+    from frenetix_motion_planner.planner import Planner
+    me = types.SimpleNamespace(coordinate_system=_ProjectingCS(cs), vehicle_params=types.SimpleNamespace(**syn.VEHICLE_2),
+                               _LOW_VEL_MODE=bool(low_vel_mode), msg_logger=_Log())
+    lon, lat = Planner._compute_initial_states(me, x_0)
+    return [float(v) for v in lon], [float(v) for v in lat]
+
+
+def initial_state_cases():
+    """Frenet initial states of random ego poses next to four reference paths, both velocity modes -> ref_initial_states.npz
+    (pins ReactivePlannerB200._compute_initial_states and the device-side frx_initial_state)."""
+    rng = np.random.default_rng(2026)
+    tj = np.load(os.path.join(HERE, "tjunction.npz"))["reference_path"]
+    paths = {"arc": syn.arc_polyline(R=60.0, M=220), "scurve": syn.scurve_polyline(M=220),
+             "straight": syn.straight_polyline(120), "tjunction": tj}
+    out = {}
+    for name, poly in paths.items():
+        cs = CoordinateSystem(poly)
+        rows = []
+        for k in range(12):
+            s, d = rng.uniform(5.0, cs.ref_pos[-1] - 40.0), rng.uniform(-2.5, 2.5)
+            X = cs.convert_to_cartesian_coords(s, d)
+            i = int(np.argmax(cs.ref_pos > s)) - 1
+            th = cs.ref_theta[i] + rng.uniform(-0.3, 0.3)
+            low = k % 3 == 0
+            v = rng.uniform(0.2, 1.9) if low else rng.uniform(2.1, 15.0)
+            x_0 = types.SimpleNamespace(position=np.array(X), orientation=float(th), velocity=float(v),
+                                        acceleration=float(rng.uniform(-2, 2)), yaw_rate=0.0,
+                                        steering_angle=float(rng.uniform(-0.2, 0.2)), time_step=0)
+            lon, lat = reference_initial_state(cs, x_0, low)
+            rows.append([X[0], X[1], x_0.orientation, x_0.velocity, x_0.acceleration, x_0.steering_angle, float(low)] + lon + lat)
+        out[f"{name}_polyline"] = poly
+        out[f"{name}_cases"] = np.array(rows)
+    np.savez_compressed(os.path.join(HERE, "ref_initial_states.npz"), **out)
+    print("initial states:", {k: v.shape for k, v in out.items() if k.endswith("_cases")})
+
+
 def tjunction_inputs():
     """Inputs of the ZAM_Tjunction-1_42_T-1 fixture (tests/golden/tjunction.npz): smoothed reference path, the
     ego's Frenet state at time step 0 and the ground-truth predictions of the five cars."""
     g = np.load(os.path.join(HERE, "tjunction.npz"))
     poly = g["reference_path"]
     cs = CoordinateSystem(poly)
-    from frenetix_motion_planner_b200.reactive_planner_b200 import ReactivePlannerB200
     x_0 = types.SimpleNamespace(position=g["ego_position_rear"], orientation=float(g["ego_orientation"]),
                                 velocity=float(g["ego_velocity"]), acceleration=float(g["ego_acceleration"]),
                                 yaw_rate=float(g["ego_yaw_rate"]), steering_angle=0.0, time_step=0)
-    me = types.SimpleNamespace(coordinate_system=cs, vehicle_params=types.SimpleNamespace(**syn.VEHICLE_2),
-                               _LOW_VEL_MODE=x_0.velocity < 2.0)
-    x_cl = ReactivePlannerB200._compute_initial_states(me, x_0)
-    x_cl = ([float(v) for v in x_cl[0]], [float(v) for v in x_cl[1]])
+    # the reference's own Frenet-state code on an independent projection -- nothing of the product is involved
+    x_cl = reference_initial_state(cs, x_0, x_0.velocity < 2.0)
     preds = []
     for o in range(g["obstacle_states"].shape[0]):
         st = g["obstacle_states"][o, 1:32]                       # time steps 1..31 (prediction_helpers.py:239-247)
@@ -250,6 +357,10 @@ def tjunction_inputs():
 
 
 if __name__ == "__main__":
+    if "--initial-states" in sys.argv:
+        initial_state_cases()
+        sampling_order_cases()
+        sys.exit(0)
     if "--tjunction" in sys.argv:
         poly, x_cl, x_0, preds = tjunction_inputs()
         print("x_cl", x_cl)
@@ -281,3 +392,5 @@ if __name__ == "__main__":
     run_case("short_hv_nodraw", short, x_cl_a, 8.0, 0.0, 8.0, False, False, 2)
     sampling_matrix_case()
     inactive_cost_case()
+    initial_state_cases()
+    sampling_order_cases()

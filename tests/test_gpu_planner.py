@@ -87,7 +87,8 @@ def test_multiproc_debug_reports_reason_counters_and_resampling_loop():
 
 def test_resampling_loop_and_last_level_fallback():
     """Nothing selectable at one level -> next level (reactive_planner.py:84-97); at the last level the
-    reference falls back to a feasible trajectory (:262-269; here: the cheapest one unless a risk function is set)."""
+    reference falls back to the feasible trajectory of lowest risk (:262-269).  Without an attached risk function the
+    planner ranks by: stays on the road, latest first collision, prediction cost, total cost."""
     g, ref, prm, preds = load_golden("scurve_brake_hv_draw")
     p = make_planner(g, prm, preds, 3.0)
     p._sampling_min = 1
@@ -102,8 +103,14 @@ def test_resampling_loop_and_last_level_fallback():
     opt = p.optimal_trajectory
     assert pair is not None and opt.feasible and opt.valid
     b = p._bundle
-    feas = ((b.flags & 3) == 3)
-    assert opt.cost == b.total[feas].min()
+    feas = np.flatnonzero((b.flags & 3) == 3)
+    f = b.flags[feas]
+    off = (f & (1 << 13)) != 0
+    first_hit = np.where((f & (1 << 12)) != 0, (f >> 18) & 63, 64).astype(np.int64)
+    pred = b.costs[feas, p.cost_names.index("prediction")]
+    keys = sorted(zip(off.tolist(), (-first_hit).tolist(), pred.tolist(), b.total[feas].tolist(), feas.tolist()))
+    assert off.all() and opt.uniqueId == keys[0][4]
+    assert opt.boundary_harm > 0 and opt.boundary_harm == 1 / (1 + np.exp(4.591 - 0.185 * opt.cartesian.v[(int(b.flags[opt.uniqueId]) >> 24) & 63]))
     p.risk_function = lambda t: -t.cost                             # user-supplied risk: prefers the most expensive
     p.plan()
     assert p.optimal_trajectory.cost == p._bundle.total[(p._bundle.flags & 3) == 3].max()
@@ -150,7 +157,9 @@ def test_tjunction_scenario_from_cartesian_state():
                           yaw_rate=float(fx["ego_yaw_rate"]), steering_angle=0.0, time_step=0)
     p.x_cl = None
     p.update_externals(reference_path=fx["reference_path"], x_0=x_0, x_cl=None, desired_velocity=8.0)
-    assert np.allclose(p.x_cl[0], g["x_cl_lon"], rtol=1e-12) and np.allclose(p.x_cl[1], g["x_cl_lat"], rtol=1e-12)
+    # golden x_cl: the reference's own _compute_initial_states on an independent projection (make_golden.py)
+    assert np.allclose(p.x_cl[0], g["x_cl_lon"], rtol=1e-9) and np.allclose(p.x_cl[1], g["x_cl_lat"], rtol=1e-9, atol=1e-12)
+    p.x_cl = (list(g["x_cl_lon"]), list(g["x_cl_lat"]))      # bit-identical sampling rows for the comparison below
     p.plan()
     ok = fo.plan(g["sampling"], ref, prm, preds, collision_check=False)["margins"] >= BAND
     opt = p.optimal_trajectory

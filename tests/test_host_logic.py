@@ -176,3 +176,46 @@ def test_reference_arm_prints_one_json_line_on_cpu():
         assert k in d, k
     assert d["impl"] == "reference" and d["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] == 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+
+
+def test_set_iteration_order_equals_the_reference_for_every_level():
+    """the row order (= uniqueId, = how equal-cost ties break) is the iteration order of the reference's SET
+    objects; a copy of a set may iterate differently.  24 random v / d / t configurations x 4 levels, python and cpp
+    style, against lists recorded from the reference's own SamplingHandler (tests/golden/ref_sampling_order.npz)."""
+    g = np.load(os.path.join(GOLDEN_DIR, "ref_sampling_order.npz"))
+    n_unsorted = 0
+    for k, (v_lo, v_hi, d_half, t_min, horizon, d0, ss0) in enumerate(g["cases"]):
+        sh = SamplingHandler(dt=0.1, max_sampling_number=4, t_min=t_min, horizon=horizon, delta_d_max=d_half,
+                             delta_d_min=-d_half, d_ego_pos=False)
+        sh.set_v_sampling(v_lo, v_hi)
+        x_cl = ([3.0, ss0, 0.0], [d0, 0.0, 0.0])
+        for lvl in range(4):
+            t, v, d = sampling_axes(sh, lvl, x_cl)
+            assert list(t) == list(g[f"c{k}_l{lvl}_t"]) and list(v) == list(g[f"c{k}_l{lvl}_v"])
+            assert list(d) == list(g[f"c{k}_l{lvl}_d"])
+            n_unsorted += list(v) != sorted(v)
+            rows = python_path_rows(t, v, d, x_cl)
+            want = [(a, b, c) for a in g[f"c{k}_l{lvl}_t"] for b in g[f"c{k}_l{lvl}_v"] for c in g[f"c{k}_l{lvl}_d"]]
+            assert np.array_equal(rows[:, [1, 5, 10]], np.array(want))
+            tc, vc, dc = sampling_axes(sh, lvl, x_cl, cpp_style=True)
+            # the cpp union value is N * dT of the reference; round(horizon / dt) * dt here: same double
+            assert list(tc) == list(g[f"c{k}_l{lvl}_t_cpp"]) and list(vc) == list(g[f"c{k}_l{lvl}_v_cpp"])
+    assert n_unsorted > 10          # the cases really exercise hash order, not sorted order
+
+
+def test_initial_frenet_state_equals_the_reference_code():
+    """planner.py:567-635: ReactivePlannerB200._compute_initial_states against the reference's OWN function run on an
+    independent projection (tests/golden/make_golden.py: initial_state_cases) -- 48 poses, both velocity modes."""
+    from types import SimpleNamespace
+    from frenetix_motion_planner_b200.reactive_planner_b200 import ReactivePlannerB200
+    from frenetix_motion_planner_b200.coordinate_system import CoordinateSystem
+    g = np.load(os.path.join(GOLDEN_DIR, "ref_initial_states.npz"))
+    for name in ("arc", "scurve", "straight", "tjunction"):
+        cs = CoordinateSystem(g[f"{name}_polyline"])
+        for row in g[f"{name}_cases"]:
+            x_0 = SimpleNamespace(position=row[:2], orientation=row[2], velocity=row[3], acceleration=row[4],
+                                  steering_angle=row[5], yaw_rate=0.0, time_step=0)
+            me = SimpleNamespace(coordinate_system=cs, vehicle_params=SimpleNamespace(**syn.VEHICLE_2), _LOW_VEL_MODE=bool(row[6]))
+            lon, lat = ReactivePlannerB200._compute_initial_states(me, x_0)
+            got, want = np.array(list(lon) + list(lat)), row[7:]
+            assert np.all(np.abs(got - want) <= 1e-9 * np.maximum(1.0, np.abs(want))), (name, got, want)
