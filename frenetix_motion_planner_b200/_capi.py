@@ -53,7 +53,8 @@ class FrxParams(C.Structure):
                 ("x0_orientation", C.c_double), ("desired_velocity", C.c_double),
                 ("n_costs", C.c_int32), ("cost_ids", C.c_int32 * FRX_MAX_COSTS),
                 ("cost_weights", C.c_double * FRX_MAX_COSTS),
-                ("store_states", C.c_int32), ("check_collisions", C.c_int32)]
+                ("store_states", C.c_int32), ("check_collisions", C.c_int32),
+                ("curvature_rate_from_v_delta", C.c_int32), ("velocity_offset_norm", C.c_int32), ("v_delta_max", C.c_double)]
 
 
 class FrxResult(C.Structure):
@@ -65,6 +66,7 @@ class FrxResult(C.Structure):
 
 
 EXPORTS = ("frx_abi_version", "frx_create", "frx_destroy", "frx_last_error", "frx_set_reference", "frx_set_params",
+           "frx_set_reference_polyline", "frx_get_reference", "frx_initial_state",
            "frx_set_time_tables", "frx_set_predictions", "frx_set_obstacle_positions", "frx_set_static_obbs",
            "frx_plan", "frx_plan_device", "frx_plan_device_async", "frx_plan_wait", "frx_plan_grid", "frx_plan_batched", "frx_state_pitch", "frx_last_launches", "frx_get_states",
            "frx_get_states_range", "frx_winner_states", "frx_get_costs", "frx_get_flags", "frx_device_pointers", "frx_winner_device_pointer",
@@ -96,6 +98,9 @@ def load_library(path: Optional[str] = None):
     lib.frx_last_error.argtypes = [vp]; lib.frx_last_error.restype = C.c_char_p
     lib.frx_set_reference.argtypes = [vp, C.c_int32, dp, dp, dp, dp, dp, dp]
     lib.frx_set_params.argtypes = [vp, C.POINTER(FrxParams)]
+    lib.frx_set_reference_polyline.argtypes = [vp, C.c_int32, dp]
+    lib.frx_get_reference.argtypes = [vp, C.c_int32, dp]
+    lib.frx_initial_state.argtypes = [vp, dp, C.c_int32, C.c_double, dp]
     lib.frx_set_time_tables.argtypes = [vp, C.c_int32, dp, ip, dp]
     lib.frx_set_predictions.argtypes = [vp, C.c_int32, C.c_int32, dp, dp, dp, dp, dp, ip]
     lib.frx_set_obstacle_positions.argtypes = [vp, C.c_int32, dp]
@@ -179,10 +184,28 @@ class Handler:
             raise ValueError("reference tables must have equal length")
         self._check(self._lib.frx_set_reference(self._ctx, M, *[_dptr(a) for a in arrs]))
 
+    def set_reference_polyline(self, polyline) -> np.ndarray:
+        """Build the six reference tables on the device from an [M, 2] polyline; returns them ([6, M]: pos, theta, curv,
+        curv_d, x, y) so that the host keeps a view of what the device plans on."""
+        xy = _f64(polyline)
+        if xy.ndim != 2 or xy.shape[1] != 2:
+            raise ValueError("polyline must be [M, 2]")
+        self._check(self._lib.frx_set_reference_polyline(self._ctx, xy.shape[0], _dptr(xy)))
+        out = np.empty((6, xy.shape[0]), dtype=np.float64)
+        self._check(self._lib.frx_get_reference(self._ctx, xy.shape[0], _dptr(out)))
+        return out
+
+    def initial_state(self, x, y, orientation, velocity, acceleration, steering_angle, low_vel_mode, wheelbase):
+        """Planner._compute_initial_states on the device -> ([s, s', s''], [d, d', d''])."""
+        x0 = _f64([x, y, orientation, velocity, acceleration, steering_angle])
+        out = np.empty(6, dtype=np.float64)
+        self._check(self._lib.frx_initial_state(self._ctx, _dptr(x0), int(bool(low_vel_mode)), float(wheelbase), _dptr(out)))
+        return [float(v) for v in out[:3]], [float(v) for v in out[3:]]
+
     def set_params(self, *, dt, N, low_vel_mode, draw_traj_set, kinematic_debug, a_max, v_switch, delta_max,
                    wheelbase, wb_rear_axle, length, width, x0_orientation, desired_velocity,
                    cost_names: Sequence[str], cost_weights: Sequence[float], store_states=True,
-                   check_collisions=True):
+                   check_collisions=True, curvature_rate_from_v_delta=False, v_delta_max=0.4, velocity_offset_norm=1):
         p = FrxParams()
         p.dt, p.N = float(dt), int(N)
         p.low_vel_mode, p.draw_traj_set, p.kinematic_debug = int(bool(low_vel_mode)), int(bool(draw_traj_set)), int(bool(kinematic_debug))
@@ -199,6 +222,8 @@ class Handler:
             p.cost_ids[k] = COST_ID[n]
             p.cost_weights[k] = float(w)
         p.store_states, p.check_collisions = int(bool(store_states)), int(bool(check_collisions))
+        p.curvature_rate_from_v_delta, p.v_delta_max = int(bool(curvature_rate_from_v_delta)), float(v_delta_max)
+        p.velocity_offset_norm = int(velocity_offset_norm)
         self._check(self._lib.frx_set_params(self._ctx, C.byref(p)))
         self.n_costs = p.n_costs
         self.Nt = int(N) + 1

@@ -27,6 +27,9 @@ void frx_launch_obstacle_compact(int O, int Tp, int Nt, const double* obs, const
                                  double* hull, float4* hull32, int* n_pred, int* n_hull, cudaStream_t st);
 void frx_launch_static_cull(int B, const double* sobb, double ox, double oy, float4* out, cudaStream_t st);
 double frx_measure_fp64_peak(int sm_count, cudaStream_t st, cudaError_t* err);
+void frx_launch_reference_tables(int M, int Mpad, const double* xy, double* tab, double* scratch, cudaStream_t st);
+void frx_launch_initial_state(int M, int Mpad, const double* tab, const double* in, double wheelbase, int low, double* out,
+                              cudaStream_t st);
 void frx_launch_collision_counter(long long N, long long row_base, const double* total, const uint32_t* flags,
                                   const FrxBest* winner, unsigned long long* counters, int grid, cudaStream_t st);
 void frx_launch_gather(const double* states, long long Np, int Nt, int Ntp, const long long* idx, long long first,
@@ -215,6 +218,57 @@ int frx_set_reference(frx_ctx* ctx, int32_t M, const double* ref_pos, const doub
     return FRX_OK;
 }
 
+int frx_set_reference_polyline(frx_ctx* ctx, int32_t M, const double* xy) {
+    if (!ctx) return FRX_ERR_INVALID;
+    REQUIRE(M >= 3 && xy, "frx_set_reference_polyline: need a polyline of at least 3 vertices");
+    CK(cudaSetDevice(ctx->device));
+    const int Mpad = (M + 1) & ~1;
+    REQUIRE(frx_eval_smem_bytes(Mpad, ctx->have_params ? ctx->prm.N + 1 : 64) <= (size_t)ctx->max_smem_optin,
+            "frx_set_reference_polyline: reference path too long for the shared-memory table");
+    DevBuf<double> in, scratch;
+    CK(in.reserve((size_t)2 * M)); CK(scratch.reserve((size_t)4 * M)); CK(ctx->ref.reserve((size_t)6 * Mpad));
+    CK(cudaMemcpyAsync(in.p, xy, sizeof(double) * 2 * M, cudaMemcpyHostToDevice, ctx->stream));
+    frx_launch_reference_tables(M, Mpad, in.p, ctx->ref.p, scratch.p, ctx->stream);
+    CK(cudaGetLastError());
+    double ends[2] = {0.0, 0.0};      // ref_pos[0] and ref_pos[M-1] for the segment-search guess
+    CK(cudaMemcpyAsync(&ends[1], ctx->ref.p + (M - 1), sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    in.release(); scratch.release();
+    ctx->M = M; ctx->Mpad = Mpad; ctx->have_ref = true;
+    ctx->inv_step = (double)(M - 1) / (ends[1] - ends[0]);
+    ctx->origin_x = xy[0]; ctx->origin_y = xy[1];
+    ctx->compact_Nt = 0; ctx->sobb32_dirty = true;
+    return FRX_OK;
+}
+
+int frx_get_reference(frx_ctx* ctx, int32_t M, double* out) {
+    if (!ctx) return FRX_ERR_INVALID;
+    REQUIRE(ctx->have_ref && M == ctx->M && out, "frx_get_reference: no reference set / wrong length");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpy2DAsync(out, sizeof(double) * M, ctx->ref.p, sizeof(double) * ctx->Mpad, sizeof(double) * M, 6,
+                         cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return FRX_OK;
+}
+
+int frx_initial_state(frx_ctx* ctx, const double* x0, int32_t low_vel_mode, double wheelbase, double* x_cl) {
+    if (!ctx) return FRX_ERR_INVALID;
+    REQUIRE(ctx->have_ref, "frx_initial_state: set the reference path first");
+    REQUIRE(x0 && x_cl && wheelbase > 0, "frx_initial_state: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->gout.reserve(16));
+    CK(cudaMemcpyAsync(ctx->gout.p, x0, sizeof(double) * 6, cudaMemcpyHostToDevice, ctx->stream));
+    frx_launch_initial_state(ctx->M, ctx->Mpad, ctx->ref.p, ctx->gout.p, wheelbase, low_vel_mode ? 1 : 0, ctx->gout.p + 8, ctx->stream);
+    CK(cudaGetLastError());
+    double h[7];
+    CK(cudaMemcpyAsync(h, ctx->gout.p + 8, sizeof(double) * 7, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int k = 0; k < 6; ++k) x_cl[k] = h[k];
+    REQUIRE(h[6] == 0.0, "Initial state or reference incorrect! Curvilinear velocity is negative which indicates that the ego "
+                         "vehicle is not driving in the same direction as specified by the reference");
+    return FRX_OK;
+}
+
 int frx_set_params(frx_ctx* ctx, const frx_params* p) {
     if (!ctx) return FRX_ERR_INVALID;
     REQUIRE(p != nullptr, "frx_set_params: null");
@@ -223,6 +277,8 @@ int frx_set_params(frx_ctx* ctx, const frx_params* p) {
     REQUIRE(p->n_costs >= 0 && p->n_costs <= FRX_MAX_COSTS, "frx_set_params: n_costs out of range");
     for (int k = 0; k < p->n_costs; ++k)
         REQUIRE(p->cost_ids[k] >= 0 && p->cost_ids[k] < FRX_NUM_COST_TERMS, "frx_set_params: unknown cost id");
+    REQUIRE(!p->curvature_rate_from_v_delta || p->v_delta_max > 0, "frx_set_params: v_delta_max must be > 0");
+    REQUIRE(p->velocity_offset_norm >= 0 && p->velocity_offset_norm <= 2, "frx_set_params: velocity_offset_norm must be 0, 1 or 2");
     if (ctx->have_params && ctx->prm.N != p->N) ctx->have_tables = false;
     ctx->prm = *p;
     ctx->kappa_max = tan(p->delta_max) / p->wheelbase;   // reactive_planner.py:492
@@ -384,6 +440,8 @@ static int prepare_plan(frx_ctx* ctx, long long N, const double* d_sampling, boo
     for (int k = 0; k < K; ++k) { a.w[k] = p.cost_weights[k]; a.cost_ids[k] = p.cost_ids[k]; }
     a.n_costs = K; a.Nt = Nt; a.Ntp = Ntp; a.low = p.low_vel_mode; a.draw = p.draw_traj_set; a.debug = p.kinematic_debug;
     a.store_states = p.store_states; a.check_collisions = p.check_collisions;
+    a.kd_from_v_delta = p.curvature_rate_from_v_delta ? 1 : 0; a.vo_norm2 = (p.velocity_offset_norm == 2) ? 1 : 0;
+    a.v_delta_over_wb = p.v_delta_max / p.wheelbase; a.wheelbase = p.wheelbase;
     a.ref = ctx->ref.p; a.M = ctx->M; a.Mpad = ctx->Mpad;
     a.Ttab = ctx->Ttab.p; a.Tlen = ctx->Tlen.p; a.tpow = ctx->tpow.p; a.nT = ctx->nT; a.tpitch = ctx->tpitch;
     a.mpitch = frx_memo_pitch_host(Nt);

@@ -63,6 +63,8 @@ struct FrxKernelArgs {
     int Nt, Ntp;            // samples per candidate, step pitch of the state tensor
     int low, draw, debug;
     int store_states, check_collisions;
+    int kd_from_v_delta, vo_norm2;      // cpp-path variants (frx_params.curvature_rate_from_v_delta / velocity_offset_norm == 2)
+    double v_delta_over_wb, wheelbase;  // v_delta_max / wheelbase and the wheelbase, for the curvature-rate limit
     // ---- reference path: 6 tables of Mpad doubles, contiguous (pos, theta, curv, curv_d, x, y)
     const double* ref;
     int M, Mpad;

@@ -218,6 +218,14 @@ __device__ __noinline__ void frx_memo_fill(const FrxKernelArgs& A, const double*
     FRX_MSTAMP(14);
 }
 
+// curvature-rate limit (:513-521): the Python path's constant 0.4, or (use_cpp flavour) v_delta_max / (wheelbase cos^2(delta))
+// with delta = atan(wheelbase kappa), i.e. (v_delta_max / wheelbase) (1 + (wheelbase kappa)^2)
+__device__ __forceinline__ double frx_kappa_dot_max(const FrxKernelArgs& A, const double kappa) {
+    if (!A.kd_from_v_delta) return 0.4;
+    const double wk = A.wheelbase * kappa;
+    return A.v_delta_over_wb * (1.0 + wk * wk);
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // one candidate, one thread
 // ------------------------------------------------------------------------------------------------------------
@@ -411,7 +419,7 @@ __device__ __forceinline__ FrxLaneOut frx_candidate(const FrxKernelArgs& A, cons
             g |= (vi < -FRX_EPS) ? 1u : 0u;
             g |= (fabs(kappa) > A.kappa_max) ? 2u : 0u;
             g |= (fabs(ddivc(rint(yaw_rate * 100000.0), 100000.0, 1e-5)) > theta_dot_max) ? 4u : 0u;
-            g |= (fabs(kappa_dot) > 0.4) ? 8u : 0u;
+            g |= (fabs(kappa_dot) > frx_kappa_dot_max(A, kappa)) ? 8u : 0u;
             g |= (!(-A.a_max <= ai && ai <= a_hi)) ? 16u : 0u;
         }
         double kd = has_prev ? (kappa - ka_prev) : 0.0;   // np.append([0], np.diff(kappa_gl))
@@ -433,7 +441,7 @@ __device__ __forceinline__ FrxLaneOut frx_candidate(const FrxKernelArgs& A, cons
             xi = 0.0; yi = 0.0; th_gl = 0.0; th_cl = 0.0; vi = 0.0; ai = 0.0; kappa = 0.0; kd = 0.0;
         }
         // running sums of the two default reductions (velocity_offset :120-130, distance_to_reference_path :154-169)
-        if (i >= half && i < Nt - 1) vo_sum += fabs(vi - A.v_des);
+        if (i >= half && i < Nt - 1) { const double dv = vi - A.v_des; vo_sum += A.vo_norm2 ? dv * dv : fabs(dv); }
         dr_sum += fabs(di);
         v_last = vi; dr_last = di;       // what is left after the loop are the values of the segment's last step (Nt - 1 for its owner)
         if (XCOST) {
@@ -464,7 +472,7 @@ __device__ __forceinline__ FrxLaneOut frx_candidate(const FrxKernelArgs& A, cons
             double yaw_rate = ddivc(th_first - th_in, dT, A.inv_dt);
             if (fabs(ddivc(rint(yaw_rate * 100000.0), 100000.0, 1e-5)) > A.kappa_max * vi_first) g_first |= 4u;
             double kappa_dot = ddivc(ka_first - ka_in, dT, A.inv_dt);
-            if (fabs(kappa_dot) > 0.4) g_first |= 8u;
+            if (fabs(kappa_dot) > frx_kappa_dot_max(A, ka_first)) g_first |= 8u;
             if (st_all) __stcs(sp + (size_t)FRX_F_KAPPA_DOT * fstride + (size_t)i0 * sstride, ka_first - ka_in);
         }
         if (XCOST) {
@@ -570,7 +578,7 @@ __device__ __forceinline__ FrxLaneOut frx_candidate(const FrxKernelArgs& A, cons
                         const int k = i - 1;                                            // hull of boxes k, k + 1
                         Hull e = obb_sum_hull(pbx, pby, pux, puy, bx, by, cs, sn, A.half_len, A.half_wid);
                         const double er = sqrt(e.ha * e.ha + e.hb * e.hb) * (1.0 + 1e-9);
-                        if (k >= 1 && !collide) {
+                        if (k >= 1 && !collide && A.O > 0) {
                             // obstacle hulls of step k - 1 (hull record: cx, cy, r | ux, uy | ha, hb)
                             const int n = __ldg(A.on_hull + (k - 1));
                             const double2* __restrict__ rec = reinterpret_cast<const double2*>(A.ohull + (size_t)(k - 1) * A.O * 8);

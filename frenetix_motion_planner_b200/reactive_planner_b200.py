@@ -113,6 +113,14 @@ class ReactivePlannerB200:
         self._kinematic_debug = bool(_get(debug, "kinematic_debug", True))
         # "cpp" sampling adds {N*dT}, {ss0} to the level sets like reactive_planner_cpp.py:235-237
         self.sampling_style = _get(debug, "sampling_style", "python")
+        # the other two things ReactivePlannerCpp does differently on the hot path (reactive_planner_cpp.py:109-112,
+        # 170-178): curvature-rate limit from vehicle.v_delta_max, velocity-offset cost with norm_order = 2
+        self.cpp_flavour = bool(_get(debug, "cpp_flavour", False))
+        if self.cpp_flavour:
+            self.sampling_style = "cpp"
+        # True: the reference tables and the Frenet initial state are computed on the device (frx_set_reference_polyline,
+        # frx_initial_state) -- no numpy / CCosy work on the host between a polyline + Cartesian state and the plan
+        self.device_frontend = bool(_get(debug, "device_frontend", False))
         self.static_obbs = None                 # road-boundary stand-in: [[cx, cy, theta, half_len, half_wid], ...]
         self.obstacle_order = None              # ids in scenario.obstacles order (collision_check.py:127-131)
         self.collision_check_enabled = True     # False: selection = first of the cost-sorted list (tests)
@@ -129,6 +137,7 @@ class ReactivePlannerB200:
         # share an existing context (and the drop-in tests substitute their recorder); nothing in the package passes it.
         self.handler = handler if handler is not None else _capi.Handler(device)
         self._bundle: Optional[TrajectoryBundle] = None
+        self._device_tables = None
         self._prefetched = None                 # (input signature, optimal trajectory) left by prefetch_plans()
         self._ref_dirty = True
         self._pred_dirty = True
@@ -161,7 +170,12 @@ class ReactivePlannerB200:
     def set_reference_and_coordinate_system(self, reference_path: np.ndarray = None, coordinate_system=None):
         """Reference tables for the device; an existing CoordinateSystem (e.g. the reference's CCosy wrapper)
         can be handed in instead of a polyline."""
-        if coordinate_system is None:
+        if coordinate_system is None and self.device_frontend:
+            ref = np.ascontiguousarray(reference_path, dtype=np.float64)
+            tab = self.handler.set_reference_polyline(ref)            # built on the device, read back once for the host view
+            coordinate_system = CoordinateSystem.from_tables(ref, tab[0], tab[1], tab[2], tab[3])
+            self._device_tables = coordinate_system
+        elif coordinate_system is None:
             coordinate_system = CoordinateSystem(reference=reference_path)
         self.coordinate_system = coordinate_system
         self.reference_path = np.asarray(coordinate_system.reference)
@@ -273,6 +287,10 @@ class ReactivePlannerB200:
     # Frenet initial state (planner.py:567-635)
     # ------------------------------------------------------------------------------------------
     def _compute_initial_states(self, x_0):
+        if getattr(self, "device_frontend", False) and getattr(self, "_device_tables", None) is self.coordinate_system:
+            return self.handler.initial_state(x_0.position[0], x_0.position[1], x_0.orientation, x_0.velocity,
+                                              getattr(x_0, "acceleration", 0.0), getattr(x_0, "steering_angle", 0.0),
+                                              self._LOW_VEL_MODE, _get(self.vehicle_params, "wheelbase"))
         cs = self.coordinate_system
         s, d = cs.convert_to_curvilinear_coords(x_0.position[0], x_0.position[1])
         s_idx = int(np.argmax(cs.ref_pos > s)) - 1
@@ -316,10 +334,13 @@ class ReactivePlannerB200:
                      wb_rear_axle=_get(vp, "wb_rear_axle"), length=_get(vp, "length"), width=_get(vp, "width"),
                      x0_orientation=self.x_0.orientation, desired_velocity=self.desired_velocity,
                      cost_names=self.cost_names, cost_weights=self.cost_weight_list, store_states=True,
-                     check_collisions=self.collision_check_enabled and (self.use_prediction or self.static_obbs is not None))
+                     check_collisions=self.collision_check_enabled and (self.use_prediction or self.static_obbs is not None),
+                     curvature_rate_from_v_delta=self.cpp_flavour, v_delta_max=_get(vp, "v_delta_max", 0.4),
+                     velocity_offset_norm=2 if self.cpp_flavour else 1)
         if self._ref_dirty:
-            ref = np.asarray(cs.reference)
-            h.set_reference(cs.ref_pos, cs.ref_theta, cs.ref_curv, cs.ref_curv_d, ref[:, 0], ref[:, 1])
+            if getattr(self, "_device_tables", None) is not cs:       # device-built tables are already where they belong
+                ref = np.asarray(cs.reference)
+                h.set_reference(cs.ref_pos, cs.ref_theta, cs.ref_curv, cs.ref_curv_d, ref[:, 0], ref[:, 1])
             self._ref_dirty = False
         if self._pred_dirty:
             packed = hotpath.pack_predictions(self.predictions, self.obstacle_order) if self.use_prediction else None

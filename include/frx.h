@@ -112,6 +112,13 @@ typedef struct frx_params {
     double cost_weights[FRX_MAX_COSTS];
     int32_t store_states;    /* 1: materialise the 14 state fields of every candidate and step in HBM (default) */
     int32_t check_collisions;/* 1: OBB sweep vs predictions / static boxes for every candidate */
+    /* ---- the use_cpp = True flavour of the reference (reactive_planner_cpp.py:96-178); all 0 = the Python path */
+    int32_t curvature_rate_from_v_delta; /* 1: |kappa_dot| <= v_delta_max / (wheelbase cos^2(steering angle)), what
+                                            CheckCurvatureRateConstraint(wheelbase, velocityDeltaMax) stands for
+                                            (reactive_planner_cpp.py:109-112; reactive_planner.py:513-515), instead of 0.4 */
+    int32_t velocity_offset_norm;        /* 2: CalculateVelocityOffsetCost(..., norm_order=2) (reactive_planner_cpp.py:170-178):
+                                            squared instead of absolute offsets over the second half of the horizon */
+    double v_delta_max;                  /* vehicle.v_delta_max (steering rate limit), used when curvature_rate_from_v_delta */
 } frx_params;
 
 typedef struct frx_result {
@@ -140,6 +147,16 @@ const char* frx_last_error(const frx_ctx* ctx);
 int frx_set_reference(frx_ctx* ctx, int32_t M, const double* ref_pos, const double* ref_theta,
                       const double* ref_curv, const double* ref_curv_d, const double* ref_x,
                       const double* ref_y);
+/* Same tables built ON THE DEVICE from the polyline [M][2] (CoordinateSystem.__init__, utils_coordinate_system.py:203-207):
+ * a host without numpy / CCosy hands over the smoothed reference path only.  frx_get_reference reads the six tables back
+ * (out[6][M]: pos, theta, curv, curv_d, x, y). */
+int frx_set_reference_polyline(frx_ctx* ctx, int32_t M, const double* xy);
+int frx_get_reference(frx_ctx* ctx, int32_t M, double* out);
+/* Planner._compute_initial_states (frenetix_motion_planner/planner.py:567-635) on the device, including the projection
+ * (x, y) -> (s, d) the reference asks CCosy for.  x0 = {x, y, orientation, velocity, acceleration, steering_angle} of the
+ * rear axle; x_cl = {s, s', s'', d, d', d''}.  FRX_ERR_INVALID if the curvilinear velocity comes out negative (the
+ * reference raises). */
+int frx_initial_state(frx_ctx* ctx, const double* x0, int32_t low_vel_mode, double wheelbase, double* x_cl);
 int frx_set_params(frx_ctx* ctx, const frx_params* p);
 /* nT distinct durations; traj_len[k] samples are valid for T_values[k]; tpow[k][p][i] (p = 0..4 for
  * t, t^2 .. t^5; i < Nt) row-major [nT][5][Nt] */

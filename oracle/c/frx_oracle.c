@@ -61,6 +61,9 @@ typedef struct {
     double w[10];
     int32_t check_all_collisions; /* 1: collision test for every candidate; 0: lazy like planner.py:329-392 */
     int32_t collision_check;      /* 0: skip the prediction collision test (selection = first of the sorted list) */
+    int32_t kd_from_v_delta;      /* cpp flavour: kappa_dot_max = v_delta_max / (wheelbase cos^2(atan(wheelbase kappa))) */
+    int32_t vo_norm;              /* 2: squared velocity offsets */
+    double v_delta_max;
 } orc_params;
 
 typedef struct {
@@ -300,8 +303,13 @@ static uint32_t eval_candidate(const env_t* E, const double* row, double* st, do
             if (!(ry == 0 && tmax == 0)) UPD(ry - tmax);
             if (ry > tmax) g |= 4u;
             double kdot = (i > 0) ? (kap[i] - kap[i - 1]) / dT : 0.;
-            UPD(fabs(kdot) - 0.4);
-            if (fabs(kdot) > 0.4) g |= 8u;
+            double kd_max = 0.4;
+            if (P->kd_from_v_delta) {       /* the algebraic form the device uses: cos^2(atan(x)) = 1 / (1 + x^2) */
+                double wk = P->wheelbase * kap[i];
+                kd_max = (P->v_delta_max / P->wheelbase) * (1.0 + wk * wk);
+            }
+            UPD(fabs(kdot) - kd_max);
+            if (fabs(kdot) > kd_max) g |= 8u;
             double a_hi = (v[i] > P->v_switch) ? P->a_max * P->v_switch / v[i] : P->a_max;
             UPD(a[i] - a_hi); UPD(a[i] + P->a_max);
             if (!(-P->a_max <= a[i] && a[i] <= a_hi)) g |= 16u;
@@ -377,7 +385,7 @@ static void eval_costs(const env_t* E, const double* st, const double* c_lon, co
         case C_LONGITUDINAL_JERK: c = sq_jerk_integral(c_lon, dT); break;
         case C_VELOCITY_OFFSET: {
             int half = Nt / 2, m = 0;
-            for (int i = half; i < Nt - 1; i++) tmp[m++] = fabs(v[i] - P->v_des);
+            for (int i = half; i < Nt - 1; i++) { double dv = v[i] - P->v_des; tmp[m++] = (P->vo_norm == 2) ? dv * dv : fabs(dv); }
             c = np_sum(tmp, m);
             double dv = v[Nt - 1] - P->v_des;
             c += fabs(dv * dv);

@@ -21,7 +21,8 @@ class OrcParams(C.Structure):
                 ("a_max", C.c_double), ("v_switch", C.c_double), ("delta_max", C.c_double), ("wheelbase", C.c_double),
                 ("wb_rear", C.c_double), ("length", C.c_double), ("width", C.c_double), ("x0_orientation", C.c_double),
                 ("v_des", C.c_double), ("n_costs", C.c_int32), ("cost_ids", C.c_int32 * 10), ("w", C.c_double * 10),
-                ("check_all_collisions", C.c_int32), ("collision_check", C.c_int32)]
+                ("check_all_collisions", C.c_int32), ("collision_check", C.c_int32),
+                ("kd_from_v_delta", C.c_int32), ("vo_norm", C.c_int32), ("v_delta_max", C.c_double)]
 
 
 class OrcResult(C.Structure):
@@ -108,6 +109,7 @@ def plan(sampling, ref: fo.RefPath, prm: fo.Params, predictions=(), static_obbs=
         P.cost_ids[k] = fo.COST_ID[nm]
         P.w[k] = prm.cost_weights[nm]
     P.check_all_collisions, P.collision_check = int(check_all_collisions), int(collision_check)
+    P.kd_from_v_delta, P.vo_norm, P.v_delta_max = int(prm.curvature_rate_from_v_delta), int(prm.velocity_offset_norm), prm.v_delta_max
     if T_values is None:
         T_values = np.unique(S[:, 1])
     Tv, Tl, tp = time_tables(T_values, prm.dt, Nt)

@@ -105,6 +105,14 @@ class Params:
     # outcomes of a candidate whose velocity profile is constructed to end at exactly 0.001 m/s (a structural tie that
     # LAPACK rounding noise decides in the reference itself): the device must reproduce one of the two.
     standstill_threshold: float = 0.001
+    # ---- the use_cpp = True flavour (reactive_planner_cpp.py:96-178).  frenetix 0.4.0's sources are not in the tree, so
+    # these follow what the reference's Python files say about them (parity unpinned):
+    # CheckCurvatureRateConstraint(wheelbase, velocityDeltaMax): the limit the Python path carries as a comment,
+    # reactive_planner.py:513-515 -- kappa_dot_max = v_delta_max / (wheelbase * cos(steering_angle) ** 2)
+    curvature_rate_from_v_delta: bool = False
+    v_delta_max: float = 0.4
+    # CalculateVelocityOffsetCost(..., norm_order=2): squared instead of absolute offsets
+    velocity_offset_norm: int = 1
 
     def active_costs(self):
         names = [k for k, w in self.cost_weights.items() if w != 0]
@@ -296,7 +304,10 @@ def _costs_for(name, st, c_lon, c_lat, prm: Params, predictions, inv_covs, Nt):
     if name == "velocity_offset":                    # :120-130
         vel = st[F_V]
         half_idx = int(len(vel) / 2)
-        cost = np.sum(np.abs(vel[half_idx:-1] - prm.desired_velocity))
+        if prm.velocity_offset_norm == 2:
+            cost = np.sum(np.square(vel[half_idx:-1] - prm.desired_velocity))
+        else:
+            cost = np.sum(np.abs(vel[half_idx:-1] - prm.desired_velocity))
         cost += np.abs(((vel[-1] - prm.desired_velocity) ** 2))
         return float(cost)
     if name == "distance_to_reference_path":         # :154-169 (len(d + 4) == len(d))
@@ -538,8 +549,12 @@ def check_feasibility_one(row, ref: RefPath, prm: Params):
                     break
 
             kappa_dot = (kappa_gl[i] - kappa_gl[i - 1]) / dT if i > 0 else 0.
-            upd(abs(kappa_dot) - 0.4)
-            if abs(kappa_dot) > 0.4:
+            kappa_dot_max = 0.4
+            if prm.curvature_rate_from_v_delta:
+                steering_angle = np.arctan2(prm.wheelbase * kappa_gl[i], 1.0)
+                kappa_dot_max = prm.v_delta_max / (prm.wheelbase * math.cos(steering_angle) ** 2)
+            upd(abs(kappa_dot) - kappa_dot_max)
+            if abs(kappa_dot) > kappa_dot_max:
                 feasible = False
                 reasons[7] = 1
                 if brk:

@@ -225,6 +225,27 @@ def inactive_cost_case():
     print("inactive costs ok")
 
 
+def refpath_cases():
+    """extend_ref_path_both_ends / smooth_ref_path of the reference (utils_coordinate_system.py:20-58,110-134) on three
+    dense centre lines -> ref_refpath.npz.  commonroad_dc's resample_polyline is stood in for by the package's resampler."""
+    import commonroad_dc.geometry.util as cdc_util                 # stub module
+    from frenetix_motion_planner_b200 import reference_path as rp
+    cdc_util.resample_polyline = rp.resample_polyline
+    import importlib
+    ucs = importlib.import_module("cr_scenario_handler.utils.utils_coordinate_system")
+    ucs.resample_polyline = rp.resample_polyline
+    tj = np.load(os.path.join(HERE, "tjunction.npz"))["centre_line"]
+    routes = {"tjunction": rp.resample_polyline(tj, 0.125), "scurve": rp.resample_polyline(syn.scurve_polyline(M=200), 0.125),
+              "arc": rp.resample_polyline(syn.arc_polyline(R=45.0, M=90), 0.125)}
+    out = {}
+    for name, route in routes.items():
+        ext = ucs.extend_ref_path_both_ends(route)
+        out[f"{name}_route"], out[f"{name}_extended"], out[f"{name}_smooth"] = route, ext, ucs.smooth_ref_path(ext)
+        out[f"{name}_extended_80"] = ucs.extend_ref_path_both_ends(route, 80)
+    np.savez_compressed(os.path.join(HERE, "ref_refpath.npz"), **out)
+    print("ref paths:", {k: v.shape for k, v in out.items() if k.endswith("_smooth")})
+
+
 def sampling_order_cases():
     """Iteration order of the reference's level SETS (python hash order: it fixes uniqueId = row index and every
     equal-cost tie) for random v / d intervals, all levels, plus the cpp path's unions -> ref_sampling_order.npz."""
@@ -360,6 +381,7 @@ if __name__ == "__main__":
     if "--initial-states" in sys.argv:
         initial_state_cases()
         sampling_order_cases()
+        refpath_cases()
         sys.exit(0)
     if "--tjunction" in sys.argv:
         poly, x_cl, x_0, preds = tjunction_inputs()
@@ -394,3 +416,4 @@ if __name__ == "__main__":
     inactive_cost_case()
     initial_state_cases()
     sampling_order_cases()
+    refpath_cases()

@@ -20,12 +20,15 @@ class OracleHandler:
     # ---- set-up (same signatures as _capi.Handler)
     def set_params(self, *, dt, N, low_vel_mode, draw_traj_set, kinematic_debug, a_max, v_switch, delta_max, wheelbase,
                    wb_rear_axle, length, width, x0_orientation, desired_velocity, cost_names, cost_weights,
-                   store_states=True, check_collisions=True):
+                   store_states=True, check_collisions=True, curvature_rate_from_v_delta=False, v_delta_max=0.4,
+                   velocity_offset_norm=1):
         self._prm = fo.Params(dt=dt, N=N, a_max=a_max, v_switch=v_switch, delta_max=delta_max, wheelbase=wheelbase,
                               wb_rear_axle=wb_rear_axle, length=length, width=width, low_vel_mode=bool(low_vel_mode),
                               x0_orientation=x0_orientation, desired_velocity=desired_velocity,
                               draw_traj_set=bool(draw_traj_set), kinematic_debug=bool(kinematic_debug),
-                              cost_weights=dict(zip(cost_names, cost_weights)))
+                              cost_weights=dict(zip(cost_names, cost_weights)),
+                              curvature_rate_from_v_delta=bool(curvature_rate_from_v_delta), v_delta_max=v_delta_max,
+                              velocity_offset_norm=int(velocity_offset_norm))
         self._check = bool(check_collisions)
         self.n_costs, self.Nt = len(cost_names), N + 1
 

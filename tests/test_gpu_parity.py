@@ -171,3 +171,20 @@ def test_step_chunked_obstacle_pass(name, chunks, monkeypatch):
         assert one[k] == cut[k], k
     assert one["res"].n_collide == cut["res"].n_collide and one["res"].n_boundary == cut["res"].n_boundary
     compare_with_oracle(cut, fo.plan(S, ref, prm, preds, static_obbs=walls), prm)
+
+
+@pytest.mark.parametrize("name", ["arc_hv_draw_pred", "scurve_lowvel_draw", "tjunction_nodraw", "scurve_brake_hv_nodraw_debug"])
+def test_cpp_flavour_switches_match_the_oracle(name):
+    """the use_cpp = True variants on the hot path -- curvature-rate limit from v_delta_max
+    (reactive_planner_cpp.py:109-112) and velocity_offset with norm_order = 2 (:170-178) -- device vs oracle, and they
+    really change the outcome."""
+    import dataclasses
+    g, ref, prm, preds = load_golden(name)
+    p2 = dataclasses.replace(prm, curvature_rate_from_v_delta=True, v_delta_max=0.4, velocity_offset_norm=2)
+    ora = fo.plan(g["sampling"], ref, p2, preds)
+    dev = device_plan(g["sampling"], ref, p2, preds)
+    compare_with_oracle(dev, ora, p2)
+    base = fo.plan(g["sampling"], ref, prm, preds)
+    assert not np.array_equal(base["flags"] & fo.FLAG_FEASIBLE, ora["flags"] & fo.FLAG_FEASIBLE)
+    k = list(ora["cost_names"]).index("velocity_offset")
+    assert not np.allclose(base["costs"][:, k], ora["costs"][:, k])

@@ -219,3 +219,20 @@ def test_initial_frenet_state_equals_the_reference_code():
             lon, lat = ReactivePlannerB200._compute_initial_states(me, x_0)
             got, want = np.array(list(lon) + list(lat)), row[7:]
             assert np.all(np.abs(got - want) <= 1e-9 * np.maximum(1.0, np.abs(want))), (name, got, want)
+
+
+def test_reference_path_preparation_equals_the_reference_code():
+    """extend_ref_path_both_ends / smooth_ref_path (utils_coordinate_system.py:20-58,110-134) against outputs of the
+    reference's own functions (tests/golden/make_golden.py: refpath_cases)."""
+    from frenetix_motion_planner_b200 import reference_path as rp
+    g = np.load(os.path.join(GOLDEN_DIR, "ref_refpath.npz"))
+    for name in ("tjunction", "scurve", "arc"):
+        ext = rp.extend_ref_path_both_ends(g[f"{name}_route"])
+        assert np.array_equal(ext, g[f"{name}_extended"])
+        assert np.array_equal(rp.extend_ref_path_both_ends(g[f"{name}_route"], 80), g[f"{name}_extended_80"])
+        sm = rp.smooth_ref_path(ext)
+        assert sm.shape == g[f"{name}_smooth"].shape and np.allclose(sm, g[f"{name}_smooth"], rtol=0, atol=1e-10)
+        seg = np.sqrt(np.sum(np.diff(sm, axis=0) ** 2, axis=1))
+        assert np.all(np.abs(seg[:-1] - 1.0) < 1e-3)                        # 1 m resampling
+    # the T-junction fixture's reference path IS this pipeline's output
+    assert np.array_equal(np.load(os.path.join(GOLDEN_DIR, "tjunction.npz"))["reference_path"], g["tjunction_smooth"])
