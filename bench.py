@@ -439,7 +439,7 @@ class Env:
 def run_gpu_workload(env: Env, name: str, steps: int, warmup: int, cpu_baseline: bool, headline: bool):
     torch, dist = env.torch, env.dist
     from frenetix_motion_planner_b200 import _capi, hotpath
-    from frenetix_motion_planner_b200.dist import ArgminExchange, shard_rows
+    from frenetix_motion_planner_b200.dist import ArgminExchange, SharedPageExchange, shard_rows, single_node
     rank, world, dev, stream = env.rank, env.world, env.dev, env.stream
     w = build_workload(name, world)
     grid_mode = w["grid_mode"]
@@ -463,7 +463,11 @@ def run_gpu_workload(env: Env, name: str, steps: int, warmup: int, cpu_baseline:
     packed = hotpath.pack_predictions(w["preds"])
     if packed is not None:
         h.set_predictions(*packed)
-    ex = ArgminExchange() if world > 1 else None
+    # the per-plan exchange of the 16-byte winner records: a shared pinned page the kernels' last CTAs write into (one node),
+    # else one NCCL all-gather (FRX_BENCH_EXCHANGE=nccl forces it)
+    use_page = world > 1 and single_node() and os.environ.get("FRX_BENCH_EXCHANGE", "page") != "nccl"
+    page = SharedPageExchange(h) if use_page else None
+    ex = ArgminExchange() if (world > 1 and not use_page) else None
     if env.fp64_peak is None:
         env.fp64_peak = h.fp64_peak_tflops()
 
@@ -476,7 +480,11 @@ def run_gpu_workload(env: Env, name: str, steps: int, warmup: int, cpu_baseline:
     launches = {"n": 0}
 
     def step_resident():
-        if grid_mode:
+        if page is not None:
+            r = (h.plan_grid(w["t1"], w["v1"], w["d1"], w["x_cl"], row_first=first, row_count=count) if grid_mode
+                 else h.plan_device(S_dev.data_ptr(), count, row_index_base=first))
+            page.finish()
+        elif grid_mode:
             r = h.plan_grid(w["t1"], w["v1"], w["d1"], w["x_cl"], row_first=first, row_count=count)
             if ex is not None:
                 ex.exchange(r.min_cost, r.argmin, handler=h)
@@ -497,7 +505,10 @@ def run_gpu_workload(env: Env, name: str, steps: int, warmup: int, cpu_baseline:
             r = h.plan_grid(w["t1"], w["v1"], w["d1"], w["x_cl"], row_first=first, row_count=count)
         else:
             r = h.plan(S_host, row_index_base=first)
-        cost, row, owner = (r.min_cost, r.argmin, 0) if ex is None else ex.exchange(r.min_cost, r.argmin, handler=h)
+        if page is not None:
+            cost, row, owner = page.finish()
+        else:
+            cost, row, owner = (r.min_cost, r.argmin, 0) if ex is None else ex.exchange(r.min_cost, r.argmin, handler=h)
         win = None
         if row >= 0 and owner == rank:
             # the selected trajectory: published by the eval kernel with the arg-min (mapped result record)
@@ -637,7 +648,10 @@ def run_gpu_workload(env: Env, name: str, steps: int, warmup: int, cpu_baseline:
                        "l2": "L2 flushed between timed iterations (256 MiB write pass, then a 256 MiB read pass that drains the dirty flush lines); per-step state output "
                              f"{count * 112 * Nt / 1e6:.0f} MB > 126 MB L2",
                        "timing": "sum of per-step CUDA-event intervals on the launch stream, max over ranks",
-                       "parallelism": f"{world} x B200, contiguous row shards, one 16-B record exchanged per rank and step" if world > 1 else "1 x B200"},
+                       "parallelism": (f"{world} x B200, contiguous row shards, one 16-B record exchanged per rank and step: " +
+                                       ("each rank's last CTA stores it into a shared pinned page (64 B posted PCIe write per rank), every host "
+                                        "reads all slots -- no collective kernel" if use_page else "one NCCL all-gather of 16 B per rank + read-back"))
+                                      if world > 1 else "1 x B200"},
             "roofline": roof_obs if dominant_obs else roof_eval,
             ("roofline_eval_kernel" if dominant_obs else "roofline_obstacle_kernel"): roof_eval if dominant_obs else roof_obs,
             "kernels_ms": {"frx_eval_kernel": eval_mean_ms, "frx_obstacle_kernel": obs_mean_ms, "both": kern_mean_ms},
@@ -678,6 +692,8 @@ def run_gpu_workload(env: Env, name: str, steps: int, warmup: int, cpu_baseline:
                           f"({S_cpu.shape[0]:,} rows, {secs:.1f} s), C/OpenMP port of the reference's Python path "
                           f"(oracle/c/frx_oracle.c, gcc -O3 -march=native -ffp-contract=off)",
                 "python_path_1core": python_path_throughput(w, S_cpu) if headline else None}
+    if page is not None:
+        page.close()
     h.close()
     del h
     torch.cuda.empty_cache()

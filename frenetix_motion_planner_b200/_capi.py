@@ -15,6 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libfrx_b200.so")
 
 FRX_MAX_COSTS = 10
+EXCHANGE_PAGE_BYTES = 8192
 NUM_FIELDS = 14
 FIELDS = ("x", "y", "theta", "v", "a", "kappa", "kappa_dot",
           "s", "d", "theta_cl", "s_dot", "s_ddot", "d_dot", "d_ddot")
@@ -70,7 +71,7 @@ EXPORTS = ("frx_abi_version", "frx_create", "frx_destroy", "frx_last_error", "fr
            "frx_set_time_tables", "frx_set_predictions", "frx_set_obstacle_positions", "frx_set_static_obbs",
            "frx_plan", "frx_plan_device", "frx_plan_device_async", "frx_plan_wait", "frx_plan_grid", "frx_plan_batched", "frx_state_pitch", "frx_last_launches", "frx_get_states",
            "frx_get_states_range", "frx_winner_states", "frx_get_costs", "frx_get_flags", "frx_device_pointers", "frx_winner_device_pointer",
-           "frx_selftest_fdiv", "frx_selftest_divc", "frx_selftest_fp64_peak", "frx_set_stream",
+           "frx_selftest_fdiv", "frx_selftest_divc", "frx_selftest_fp64_peak", "frx_set_exchange", "frx_exchange_wait", "frx_set_stream",
            "frx_synchronize")
 
 _lib = None
@@ -124,6 +125,8 @@ def load_library(path: Optional[str] = None):
     lib.frx_selftest_fdiv.argtypes = [vp, C.c_int64, dp, dp, dp, dp]
     lib.frx_selftest_divc.argtypes = [vp, C.c_int64, dp, C.c_double, dp, dp]
     lib.frx_selftest_fp64_peak.argtypes = [vp, dp]
+    lib.frx_set_exchange.argtypes = [vp, vp, C.c_int32, C.c_int32]
+    lib.frx_exchange_wait.argtypes = [vp, C.c_int64, dp, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]
     lib.frx_set_stream.argtypes = [vp, vp]
     lib.frx_synchronize.argtypes = [vp]
     for name in EXPORTS:
@@ -394,6 +397,16 @@ class Handler:
         v = C.c_double()
         self._check(self._lib.frx_selftest_fp64_peak(self._ctx, C.byref(v)))
         return float(v.value)
+
+    def set_exchange(self, page_address: Optional[int], rank: int = 0, world: int = 1):
+        """Attach the node's shared exchange page (EXCHANGE_PAGE_BYTES of zeroed POSIX shm); None detaches."""
+        self._check(self._lib.frx_set_exchange(self._ctx, C.c_void_p(page_address) if page_address else None, int(rank), int(world)))
+
+    def exchange_wait(self, timeout_us: int = 20_000_000):
+        """-> (global min cost, global row, owner rank) once every rank's record of the last plan has arrived."""
+        c, r, o = C.c_double(), C.c_int64(), C.c_int32()
+        self._check(self._lib.frx_exchange_wait(self._ctx, int(timeout_us), C.byref(c), C.byref(r), C.byref(o)))
+        return float(c.value), int(r.value), int(o.value)
 
     def winner_device_pointer(self) -> int:
         p = C.c_void_p()

@@ -5,6 +5,7 @@
 #include <math.h>
 #include <stdint.h>
 #include <string.h>
+#include <time.h>
 
 #include <new>
 #include <string>
@@ -94,6 +95,11 @@ struct frx_ctx {
     DevBuf<FrxKernelArgs> batch_args; DevBuf<int> batch_cta;
     HostResult* h_res = nullptr;       // pinned + mapped
     HostResult* d_res = nullptr;       // device address of h_res
+    FrxXchgSlot* xchg_host = nullptr;  // the node's shared exchange page (host view / device view), see frx_set_exchange
+    FrxXchgSlot* xchg_dev = nullptr;
+    int xchg_rank = 0, xchg_world = 1;
+    bool xchg_registered = false;
+    unsigned long long xchg_epoch = 0; // epoch of the last plan enqueued with the exchange attached
     bool pending = false;              // an asynchronous plan is in flight on `stream`
     bool counters_dirty = true;        // counters must be zeroed before the next launch (first use / after an error)
 
@@ -169,6 +175,7 @@ int frx_destroy(frx_ctx* ctx) {
     ctx->sobb.release(); ctx->raw_sobb.release(); ctx->sampling.release(); ctx->grid.release();
     ctx->states.release(); ctx->costs.release(); ctx->total.release(); ctx->flags.release(); ctx->traj_len.release();
     ctx->blockcnt.release(); ctx->obs_part.release(); ctx->obs_hit.release(); ctx->blockbest.release(); ctx->winner.release(); ctx->counters.release(); ctx->gidx.release(); ctx->gout.release(); ctx->batch_args.release(); ctx->batch_cta.release();
+    if (ctx->xchg_registered) cudaHostUnregister(ctx->xchg_host);
     if (ctx->h_res) cudaFreeHost(ctx->h_res);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -457,6 +464,7 @@ static int prepare_plan(frx_ctx* ctx, long long N, const double* d_sampling, boo
     a.seg = seg; a.Np = Np; a.nf_store = p.store_states ? FRX_NUM_FIELDS : 3; a.keep_xyt = (!p.store_states && need_xyt) ? 1 : 0;
     a.traj_len = ctx->traj_len.p; a.blockbest = ctx->blockbest.p; a.blockcnt = ctx->blockcnt.p; a.counters = ctx->counters.p;
     a.winner = ctx->winner.p; a.host_res = ctx->d_res; a.n_cta = grid;
+    a.xchg = nullptr; a.xchg_rank = ctx->xchg_rank; a.xchg_epoch = 0;
     if (ctx->counters_dirty) {
         CK(cudaMemsetAsync(ctx->counters.p, 0, sizeof(unsigned long long) * FRX_NUM_COUNTERS, st));
         ctx->counters_dirty = false;
@@ -546,6 +554,7 @@ static int enqueue_plan(frx_ctx* ctx, long long N, const double* d_sampling, boo
 #endif
     rc = choose_obstacle_split(ctx, &a, grid);
     if (rc != FRX_OK) return rc;
+    if (ctx->xchg_dev) { a.xchg = ctx->xchg_dev; a.xchg_epoch = ++ctx->xchg_epoch; }
     ctx->last_launches = 1;
     CK(cudaEventRecord(ctx->evk0, st));
     CK(frx_launch_eval(a, Nt, grid, st));
@@ -856,6 +865,56 @@ int frx_selftest_divc(frx_ctx* ctx, int64_t n, const double* a, double b, double
     CK(cudaMemcpyAsync(q_ieee, buf.p + 2 * n, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     buf.release();
+    return FRX_OK;
+}
+
+static_assert(FRX_XCHG_PAGE_BYTES == FRX_EXCHANGE_PAGE_BYTES, "exchange page size");
+
+int frx_set_exchange(frx_ctx* ctx, void* page, int32_t rank, int32_t world) {
+    if (!ctx) return FRX_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->xchg_registered) { cudaHostUnregister(ctx->xchg_host); ctx->xchg_registered = false; }
+    ctx->xchg_host = ctx->xchg_dev = nullptr; ctx->xchg_epoch = 0;
+    if (!page) return FRX_OK;
+    REQUIRE(world >= 1 && world <= FRX_XCHG_MAX_RANKS && rank >= 0 && rank < world, "frx_set_exchange: bad rank / world size");
+    cudaError_t e = cudaHostRegister(page, FRX_XCHG_PAGE_BYTES, cudaHostRegisterMapped | cudaHostRegisterPortable);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) cudaGetLastError();      // another context of this process did it
+    else { CK(e); ctx->xchg_registered = true; }
+    void* d = nullptr;
+    CK(cudaHostGetDevicePointer(&d, page, 0));
+    ctx->xchg_host = (FrxXchgSlot*)page; ctx->xchg_dev = (FrxXchgSlot*)d;
+    ctx->xchg_rank = rank; ctx->xchg_world = world;
+    return FRX_OK;
+}
+
+int frx_exchange_wait(frx_ctx* ctx, int64_t timeout_us, double* min_cost, int64_t* global_row, int32_t* owner_rank) {
+    if (!ctx) return FRX_ERR_INVALID;
+    REQUIRE(ctx->xchg_host && ctx->xchg_epoch > 0, "frx_exchange_wait: no exchange attached / no plan issued");
+    REQUIRE(!ctx->pending, "frx_exchange_wait: wait for the plan first (frx_plan_wait)");
+    const unsigned long long e = ctx->xchg_epoch;
+    volatile FrxXchgSlot* slots = ctx->xchg_host + (e & 1ULL) * FRX_XCHG_MAX_RANKS;
+    timespec t0; clock_gettime(CLOCK_MONOTONIC, &t0);
+    for (int r = 0; r < ctx->xchg_world; ++r) {
+        unsigned spins = 0;
+        while (__atomic_load_n(&slots[r].epoch, __ATOMIC_ACQUIRE) != e) {
+            if ((++spins & 1023u) == 0) {
+                timespec t1; clock_gettime(CLOCK_MONOTONIC, &t1);
+                const int64_t us = (int64_t)(t1.tv_sec - t0.tv_sec) * 1000000 + (t1.tv_nsec - t0.tv_nsec) / 1000;
+                if (timeout_us > 0 && us > timeout_us) {
+                    ctx->err = "frx_exchange_wait: timed out waiting for rank " + std::to_string(r) + " (epoch " + std::to_string(e) + ")";
+                    return FRX_ERR_CUDA;
+                }
+            }
+        }
+    }
+    double bc = INFINITY; long long bi = -1; int owner = -1;
+    for (int r = 0; r < ctx->xchg_world; ++r) {
+        const double c = slots[r].cost; const long long i = slots[r].idx;
+        if (i >= 0 && (bi < 0 || c < bc || (c == bc && i < bi))) { bc = c; bi = i; owner = r; }
+    }
+    if (min_cost) *min_cost = bc;
+    if (global_row) *global_row = bi;
+    if (owner_rank) *owner_rank = owner;
     return FRX_OK;
 }
 

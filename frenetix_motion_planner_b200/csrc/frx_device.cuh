@@ -46,6 +46,27 @@ struct FrxHostResult {
     double winner_states[FRX_NUM_FIELDS][64];   // the selected candidate's state rows (Nt <= 64 samples each)
 };
 
+// Multi-GPU arg-min exchange without a collective kernel: ONE page of pinned host memory shared by the ranks of a node
+// (POSIX shm, registered with every rank's CUDA context).  The last CTA of a plan stores its rank's winner record into its
+// slot -- a posted PCIe write, the same mechanism as the result record -- and every rank's host reads all slots.  Slots are
+// double-buffered by the parity of the plan epoch (a fast rank can be at most one plan ahead of a slow reader).
+struct FrxXchgSlot {
+    double cost;
+    long long idx;                  // global row, -1 = no candidate
+    unsigned long long epoch;       // written LAST (after a system-scope fence): the record of plan `epoch` is complete
+    unsigned long long pad[5];      // one slot per 64-byte line
+};
+#define FRX_XCHG_MAX_RANKS 64
+#define FRX_XCHG_PAGE_BYTES (2 * FRX_XCHG_MAX_RANKS * sizeof(FrxXchgSlot))
+
+__device__ __forceinline__ void frx_publish_exchange(FrxXchgSlot* page, int rank, unsigned long long epoch, double cost, long long idx) {
+    if (page == nullptr) return;
+    volatile FrxXchgSlot* s = page + (epoch & 1ULL) * FRX_XCHG_MAX_RANKS + rank;
+    s->cost = cost; s->idx = idx;
+    __threadfence_system();
+    s->epoch = epoch;
+}
+
 // state tensor index: blocks of 32 candidates, [block][step][field][32] (nf = fields stored per step: 14, or 3 when only
 // x, y, theta are kept for the obstacle pass)
 __host__ __device__ inline size_t frx_state_index(long long row, int Nt, int nf, int f, int i) {
@@ -120,4 +141,7 @@ struct FrxKernelArgs {
     FrxHostResult* host_res;// device address of the mapped host result struct
     unsigned long long* trace;  // FRX_TRACE tuning builds: [warps][8] globaltimer stamps, else null
     int n_cta;              // CTAs working on this plan (grid size, or this agent's share of a batched grid)
+    FrxXchgSlot* xchg;      // device address of the node's shared exchange page, or null
+    int xchg_rank;
+    unsigned long long xchg_epoch;
 };

@@ -980,6 +980,7 @@ __device__ __forceinline__ void frx_tile_body(const FrxKernelArgs& A, const int 
             if (b.idx >= 0) b.idx += A.row_base;   // the winner record carries the GLOBAL row index
             *A.winner = b;
             A.host_res->winner = b;
+            frx_publish_exchange(A.xchg, A.xchg_rank, A.xchg_epoch, b.cost, b.idx);
         } else if (threadIdx.x >= 32 && threadIdx.x < 32 + NC) {
             const int c = threadIdx.x - 32;
             unsigned long long tot = 0;

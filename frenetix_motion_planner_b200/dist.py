@@ -7,6 +7,13 @@ op = argmin" is ONE all-gather of the 16-byte winner record per rank followed by
 deterministic reduction on every rank (lowest cost, ties -> lowest global row): semantically an
 all-reduce, one collective call, latency bound over NVLink/NVSwitch.
 
+Two transports.  On one node (the default) the ranks share ONE page of pinned host memory (:class:`SharedPageExchange`):
+the last CTA of every plan stores its rank's record into its slot of that page next to the result record -- a posted
+PCIe write of one 64-byte line -- and every rank's host reads all slots after it has waited for its own plan.  No
+collective kernel, no second device round trip: the payload is 16 bytes destined for the CPUs, so system memory is the
+short way and NVLink would be a detour through a second GPU.  Across nodes (or on request) the exchange is the NCCL
+all-gather of :class:`ArgminExchange`.
+
 With the ``nccl`` backend the payload is the winner record in HBM itself (the device address the
 library exposes through ``frx_winner_device_pointer``), so there is no host round trip before the
 collective; with ``gloo`` (CPU tests) the record comes from the host result.
@@ -122,3 +129,58 @@ class ArgminExchange:
         c, r = reduce_winners(costs, rows)
         owner = int(np.nonzero(rows == r)[0][0]) if r >= 0 else -1
         return c, r, owner
+
+
+def single_node() -> bool:
+    """True when every rank of the default group runs on this node (torchrun exports LOCAL_WORLD_SIZE)."""
+    import os
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    return int(os.environ.get("LOCAL_WORLD_SIZE", str(world))) == world
+
+
+class SharedPageExchange:
+    """Arg-min exchange through one page of POSIX shared memory registered with every rank's CUDA context
+    (``frx_set_exchange`` / ``frx_exchange_wait``, include/frx.h).  torch.distributed is only used once, to agree on the
+    name of the page; the per-plan exchange involves no collective."""
+
+    def __init__(self, handler, group=None):
+        import ctypes
+        import mmap
+        import os
+        import uuid
+        import torch.distributed as dist
+        from . import _capi
+        self.handler = handler
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        name = [f"/dev/shm/frx_xchg_{uuid.uuid4().hex}" if self.rank == 0 else None]
+        if self.world > 1:
+            dist.broadcast_object_list(name, src=0, group=group)
+        self.path = name[0]
+        if self.rank == 0:
+            fd = os.open(self.path, os.O_CREAT | os.O_EXCL | os.O_RDWR, 0o600)
+            os.ftruncate(fd, _capi.EXCHANGE_PAGE_BYTES)                    # zero-filled by the kernel
+        if self.world > 1:
+            dist.barrier(group=group)
+        if self.rank != 0:
+            fd = os.open(self.path, os.O_RDWR)
+        self._mm = mmap.mmap(fd, _capi.EXCHANGE_PAGE_BYTES)
+        os.close(fd)
+        self._keep = ctypes.c_char.from_buffer(self._mm)
+        handler.set_exchange(ctypes.addressof(self._keep), self.rank, self.world)
+        if self.world > 1:
+            dist.barrier(group=group)                                      # every rank attached before the first plan
+        if self.rank == 0:
+            os.unlink(self.path)                                           # the mappings keep the page alive
+        self.bytes_per_rank_and_plan = 64
+
+    def finish(self):
+        """After the local plan has been waited for: (global min cost, global row, owner rank)."""
+        return self.handler.exchange_wait()
+
+    def close(self):
+        if self._mm is not None:
+            self.handler.set_exchange(None)
+            del self._keep
+            self._mm.close()
+            self._mm = None

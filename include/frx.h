@@ -218,6 +218,16 @@ int frx_device_pointers(frx_ctx* ctx, void** states, void** costs, void** total,
 /* device address of the 16-byte winner record {double min_cost; int64 global_row} of the last plan:
  * the payload of the multi-GPU arg-min exchange (all-gather of 16 B per rank, no host round trip) */
 int frx_winner_device_pointer(frx_ctx* ctx, void** winner);
+/* Multi-GPU arg-min exchange without a collective kernel (one node): `page` is FRX_EXCHANGE_PAGE_BYTES of host memory
+ * SHARED by the ranks (POSIX shm), zero-initialised once.  After frx_set_exchange the last CTA of every plan on this
+ * context also stores {min_cost, global row, epoch} into this rank's slot of the page (a posted PCIe write next to the
+ * result record), and frx_exchange_wait -- called after the plan has been waited for -- spins until every rank's slot
+ * shows the same plan epoch, then reduces them deterministically (lowest cost, ties -> lowest global row): semantically
+ * the all-reduce(argmin) of SURVEY 8e, with no NCCL launch, no second device round trip and 64 B per rank on the wire.
+ * All ranks must issue the same sequence of plans.  page = NULL detaches. */
+#define FRX_EXCHANGE_PAGE_BYTES 8192
+int frx_set_exchange(frx_ctx* ctx, void* page, int32_t rank, int32_t world);
+int frx_exchange_wait(frx_ctx* ctx, int64_t timeout_us, double* min_cost, int64_t* global_row, int32_t* owner_rank);
 /* diagnostics: the kernels' slow-path-free fp64 division next to IEEE division (tests only) */
 int frx_selftest_fdiv(frx_ctx* ctx, int64_t n, const double* a, const double* b, double* q_fdiv, double* q_ieee);
 /* diagnostics: the kernels' division by a plan constant b (dt, 100000, Nt; reciprocal precomputed on the host)
