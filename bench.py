@@ -392,6 +392,78 @@ def run_config4(args, w, local_rank):
         "gpu_launches": args.steps * (1 + len(handlers))}
 
 
+def planner_e2e(local_rank: int):
+    """The public Python API a user of the reference calls: ReactivePlannerB200.plan() end to end (host work, H2D of the
+    sampling axes, kernels, D2H of the result record and the selected trajectory, output conversion to the trajectory
+    pair), wall clock per call.  (a) configs[0]: the ZAM_Tjunction-1_42_T-1 fixture at the reference's default sampling
+    (630 candidates, 5 predicted cars, road boundary), with the reference's default debug flags (draw_traj_set=True keeps
+    the cost-sorted candidate set for visualisation) and without; (b) the configs[2] grid (200,000 candidates,
+    20 obstacles) through the same call."""
+    import types
+    from frenetix_motion_planner_b200 import ReactivePlannerB200
+    out = {}
+    gold = os.path.join(ROOT, "tests", "golden")
+    fx = np.load(os.path.join(gold, "tjunction.npz"))
+    raw = json.load(open(os.path.join(gold, "tjunction_lanelets.json")))
+    lanelets = {int(k): dict(left=np.array(v["left"]), right=np.array(v["right"]), adj_left=v["adj_left"], adj_right=v["adj_right"])
+                for k, v in raw.items()}
+
+    def make(draw, horizon=3.0, d_levels=None):
+        cfg_plan = types.SimpleNamespace(
+            planning=types.SimpleNamespace(planning_horizon=horizon, dt=0.1, low_vel_mode_threshold=2.0, sampling_min=2, sampling_max=3,
+                                           t_min=1.1, d_min=-3, d_max=3, d_ego_pos=False, replanning_frequency=3),
+            debug=types.SimpleNamespace(multiproc=True, num_workers=6, draw_traj_set=draw, kinematic_debug=draw, save_all_traj=False,
+                                        log_risk=False),
+            cost=types.SimpleNamespace(cost_weights=dict(syn.DEFAULT_COST_WEIGHTS)))
+        return ReactivePlannerB200(cfg_plan, types.SimpleNamespace(vehicle=types.SimpleNamespace(**syn.VEHICLE_2)), None, None, None, None,
+                                   None, device=local_rank)
+
+    def timeit(p, n=200, warm=20):
+        for _ in range(warm):
+            pair = p.plan()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            pair = p.plan()
+        dt = (time.perf_counter() - t0) / n
+        return dt, pair
+
+    preds = {}
+    for o, oid in enumerate(fx["obstacle_ids"]):
+        st = fx["obstacle_states"][o, 1:32]
+        preds[int(oid)] = {"pos_list": st[:, :2].copy(), "cov_list": np.tile(np.array([[0.1, 0.0], [0.0, 0.1]]), (31, 1, 1)),
+                           "orientation_list": st[:, 2].copy(), "v_list": st[:, 3].copy(),
+                           "shape": {"length": float(fx["obstacle_shapes"][o, 0]) + 0.5, "width": float(fx["obstacle_shapes"][o, 1]) + 0.2}}
+    x_0 = types.SimpleNamespace(position=fx["ego_position_rear"], orientation=float(fx["ego_orientation"]), velocity=float(fx["ego_velocity"]),
+                                acceleration=float(fx["ego_acceleration"]), yaw_rate=float(fx["ego_yaw_rate"]), steering_angle=0.0, time_step=0)
+    for draw in (True, False):
+        p = make(draw)
+        p.obstacle_order = [int(i) for i in fx["obstacle_ids"]]
+        p.set_road_boundary(lanelets)
+        p.update_externals(reference_path=fx["reference_path"], x_0=x_0, x_cl=None, desired_velocity=8.0, predictions=preds)
+        dt, pair = timeit(p)
+        out["config1_draw_traj_set" if draw else "config1"] = {
+            "us_per_plan": dt * 1e6, "candidates": int(p._total_count), "candidates_per_s": p._total_count / dt,
+            "selected": int(p.optimal_trajectory.uniqueId), "eval_kernel_us": 1e3 * float(p.last_plan_stats.eval_kernel_ms),
+            "obstacles": len(preds), "road_boundary_boxes": int(len(p.static_obbs))}
+        p.handler.close()
+    # (b) the configs[2] grid through plan(): the planner's level sets replaced by the dense axes
+    w = build_workload("config3", 1)
+    p = make(False)
+    cs_poly = w["polyline"]
+    x_0b = types.SimpleNamespace(position=None, orientation=w["x0_orientation"], velocity=w["v0"], acceleration=0.0, yaw_rate=0.0,
+                                 steering_angle=0.0, time_step=0)
+    p.update_externals(reference_path=cs_poly, x_0=x_0b, x_cl=w["x_cl"], desired_velocity=w["v_des"],
+                       predictions={100 + i: q for i, q in enumerate(w["preds"])})
+    dense = (w["t1"], w["v1"], w["d1"])
+    p._level_axes = lambda samp_level: dense
+    dt, pair = timeit(p, n=50, warm=5)
+    out["config3_grid"] = {"us_per_plan": dt * 1e6, "candidates": int(p._total_count), "candidates_per_s": p._total_count / dt,
+                           "selected": int(p.optimal_trajectory.uniqueId), "obstacles": len(w["preds"]),
+                           "eval_kernel_us": 1e3 * float(p.last_plan_stats.eval_kernel_ms)}
+    p.handler.close()
+    return out
+
+
 def hbm_peak():
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
@@ -743,6 +815,8 @@ def main():
                 also[name] = l2
         if rank == 0:
             line["also"] = also
+    if rank == 0 and world == 1 and not args.no_also:
+        line["e2e"]["planner"] = planner_e2e(env.local_rank)
     if rank == 0:
         emit(line)
     if world > 1:

@@ -138,6 +138,8 @@ class ReactivePlannerB200:
         self.handler = handler if handler is not None else _capi.Handler(device)
         self._bundle: Optional[TrajectoryBundle] = None
         self._device_tables = None
+        self._static_dirty = True
+        self._tables_key = None                 # durations the device's time tables were last built for
         self._prefetched = None                 # (input signature, optimal trajectory) left by prefetch_plans()
         self._ref_dirty = True
         self._pred_dirty = True
@@ -199,6 +201,7 @@ class ReactivePlannerB200:
 
     def set_static_obstacles(self, obbs):
         self.static_obbs = None if obbs is None else np.asarray(obbs, dtype=np.float64).reshape(-1, 5)
+        self._static_dirty = True
 
     def set_x_0(self, x_0):
         self.x_0 = x_0
@@ -349,7 +352,9 @@ class ReactivePlannerB200:
             else:
                 h.set_predictions(*packed)
             self._pred_dirty = False
-        h.set_static_obbs(self.static_obbs)
+        if self._static_dirty:                   # uploads synchronise the stream: only when something changed
+            h.set_static_obbs(self.static_obbs)
+            self._static_dirty = False
         if "distance_to_obstacles" in self.cost_names:
             h.set_obstacle_positions(getattr(self, "obstacle_positions", None))
 
@@ -372,7 +377,10 @@ class ReactivePlannerB200:
         axes = self._level_axes(samp_level)
         self._total_count = axes[0].size * axes[1].size * axes[2].size
         self._bundle = None                      # device buffers are recycled by the next plan
-        self.handler.set_time_tables(*hotpath.time_tables(np.unique(axes[0]), self.dT, self.N + 1))
+        key = (tuple(np.sort(axes[0]).tolist()), self.N)
+        if key != self._tables_key:              # the level's durations only change with the sampling parameters
+            self.handler.set_time_tables(*hotpath.time_tables(np.unique(axes[0]), self.dT, self.N + 1))
+            self._tables_key = key
         return python_path_rows(*axes, self.x_cl) if as_matrix else axes
 
     def _make_bundle(self, sampling=None, axes=None) -> TrajectoryBundle:
