@@ -70,7 +70,7 @@ EXPORTS = ("frx_abi_version", "frx_create", "frx_destroy", "frx_last_error", "fr
            "frx_set_reference_polyline", "frx_get_reference", "frx_initial_state",
            "frx_set_time_tables", "frx_set_predictions", "frx_set_obstacle_positions", "frx_set_static_obbs",
            "frx_plan", "frx_plan_device", "frx_plan_device_async", "frx_plan_wait", "frx_plan_grid", "frx_plan_batched", "frx_state_pitch", "frx_last_launches", "frx_get_states",
-           "frx_get_states_range", "frx_winner_states", "frx_get_costs", "frx_get_flags", "frx_device_pointers", "frx_winner_device_pointer",
+           "frx_get_states_range", "frx_winner_states", "frx_winner_record", "frx_get_costs", "frx_get_flags", "frx_device_pointers", "frx_winner_device_pointer",
            "frx_selftest_fdiv", "frx_selftest_divc", "frx_selftest_fp64_peak", "frx_set_exchange", "frx_exchange_wait", "frx_set_stream",
            "frx_synchronize")
 
@@ -118,6 +118,7 @@ def load_library(path: Optional[str] = None):
     lib.frx_get_states.argtypes = [vp, C.c_int64, C.POINTER(C.c_int64), C.c_uint32, dp]
     lib.frx_get_states_range.argtypes = [vp, C.c_int64, C.c_int64, C.c_uint32, dp]
     lib.frx_winner_states.argtypes = [vp, C.c_uint32, dp]
+    lib.frx_winner_record.argtypes = [vp, C.POINTER(C.c_uint32), ip, dp, dp]
     lib.frx_get_costs.argtypes = [vp, C.c_int64, C.c_int64, dp, dp]
     lib.frx_get_flags.argtypes = [vp, C.c_int64, C.c_int64, C.POINTER(C.c_uint32), ip]
     lib.frx_device_pointers.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
@@ -350,6 +351,13 @@ class Handler:
         out = np.empty((nf, pitch), dtype=np.float64)
         self._check(self._lib.frx_winner_states(self._ctx, mask, _dptr(out)))
         return out[:, :self.Nt]
+
+    def winner_record(self):
+        """(flags, traj_len, total cost, unweighted cost terms) of the selected candidate, from the mapped result record."""
+        fl, tl, tot = C.c_uint32(), C.c_int32(), C.c_double()
+        costs = np.empty(max(self.n_costs, 1), dtype=np.float64)
+        self._check(self._lib.frx_winner_record(self._ctx, C.byref(fl), C.byref(tl), C.byref(tot), _dptr(costs)))
+        return int(fl.value), int(tl.value), float(tot.value), costs[:self.n_costs]
 
     def get_states_range(self, first=0, count=None, fields=None) -> np.ndarray:
         count = self.n_rows - first if count is None else count

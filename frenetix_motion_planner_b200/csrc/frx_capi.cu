@@ -795,6 +795,17 @@ int frx_winner_states(frx_ctx* ctx, uint32_t field_mask, double* out) {
     return FRX_OK;
 }
 
+int frx_winner_record(frx_ctx* ctx, uint32_t* flags, int32_t* traj_len, double* total, double* costs) {
+    if (!ctx) return FRX_ERR_INVALID;
+    REQUIRE(ctx->lastN > 0 && !ctx->pending, "frx_winner_record: no finished plan");
+    REQUIRE(ctx->h_res->winner.idx >= 0, "frx_winner_record: the last plan selected no candidate");
+    if (flags) *flags = ctx->h_res->winner_flags;
+    if (traj_len) *traj_len = ctx->h_res->winner_traj_len;
+    if (total) *total = ctx->h_res->winner.cost;
+    if (costs) for (int k = 0; k < ctx->lastK; ++k) costs[k] = ctx->h_res->winner_costs[k];
+    return FRX_OK;
+}
+
 int frx_get_states_range(frx_ctx* ctx, int64_t first, int64_t count, uint32_t field_mask, double* out) {
     if (!ctx) return FRX_ERR_INVALID;
     REQUIRE(ctx->lastN > 0 && ctx->last_all_fields, "frx_get_states_range: no materialised states");

@@ -44,7 +44,21 @@ struct FrxHostResult {
     FrxBest winner;
     unsigned long long counters[FRX_NUM_COUNTERS];
     double winner_states[FRX_NUM_FIELDS][64];   // the selected candidate's state rows (Nt <= 64 samples each)
+    double winner_costs[FRX_MAX_COSTS];         // ... its unweighted cost terms, flags and sample count: everything a
+    unsigned int winner_flags;                  //     TrajectorySample of the winner can be asked for, without a second
+    int winner_traj_len;                        //     device round trip
 };
+
+// the last CTA copies the selected candidate's scalars into the mapped result record (thread 0 of the finishing block)
+#define FRX_PUBLISH_WINNER_SCALARS(A, wi)                                                          \
+    do {                                                                                           \
+        if ((wi) >= 0) {                                                                           \
+            (A).host_res->winner_flags = __ldcg((A).flags + (wi));                                 \
+            (A).host_res->winner_traj_len = __ldcg((A).traj_len + (wi));                           \
+            for (int k_ = 0; k_ < (A).n_costs; ++k_)                                               \
+                (A).host_res->winner_costs[k_] = __ldcg((A).costs + (size_t)(wi) * (A).n_costs + k_); \
+        }                                                                                          \
+    } while (0)
 
 // Multi-GPU arg-min exchange without a collective kernel: ONE page of pinned host memory shared by the ranks of a node
 // (POSIX shm, registered with every rank's CUDA context).  The last CTA of a plan stores its rank's winner record into its

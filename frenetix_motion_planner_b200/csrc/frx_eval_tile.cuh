@@ -59,6 +59,7 @@ struct FrxMemoHdr {        // one per memo slot (shared memory)
 };
 
 #define FRX_MEMO_SLOTS 2
+#define FRX_WALL_LIST 512      // static boxes a tile-level cull list can hold (more: every box is tested)
 
 __host__ __device__ inline int frx_memo_pitch(int Nt) { return (Nt + 3) & ~3; }
 __host__ __device__ inline size_t frx_tile_smem_bytes(int Mpad, int tpitch, int mpitch) {
@@ -243,7 +244,7 @@ __device__ __forceinline__ FrxLaneOut frx_candidate(const FrxKernelArgs& A, cons
                                                     const long long r, const double T, const double d0, const double dd0,
                                                     const double ddd0, const double d1, const double dd1, const double ddd1,
                                                     const double* __restrict__ mt, const FrxMemoHdr* __restrict__ H,
-                                                    const double* __restrict__ s_tp) {
+                                                    const double* __restrict__ s_tp, unsigned short* __restrict__ wall_list) {
     constexpr int C = 32 / SEG;                 // candidates per tile
     const int lane = threadIdx.x & 31;
     const int cand = lane & (C - 1), seg = lane / C;
@@ -327,6 +328,8 @@ __device__ __forceinline__ FrxLaneOut frx_candidate(const FrxKernelArgs& A, cons
         }
     }
     double vo_sum = 0.0, v_last = 0.0, dr_sum = 0.0, dr_last = 0.0;
+    // bounding box of this lane's stored positions (fused obstacle pass: tile-level cull of the static boxes)
+    float bb_x0 = 3e38f, bb_x1 = -3e38f, bb_y0 = 3e38f, bb_y1 = -3e38f;
     const int half = Nt / 2;
     // state tensor: blocks of 32 candidates, [block][step][field][32] -- the 14 fields of a step are 14 consecutive
     // 256-byte rows, so a warp's stores of one step are one 3.5 KB span addressed as base + immediate
@@ -454,6 +457,10 @@ __device__ __forceinline__ FrxLaneOut frx_candidate(const FrxKernelArgs& A, cons
             }
             a_prev = ai; thc_prev = th_cl;
         }
+        if (OBS) {
+            const float fxi = (float)(xi - A.origin_x), fyi = (float)(yi - A.origin_y);
+            bb_x0 = fminf(bb_x0, fxi); bb_x1 = fmaxf(bb_x1, fxi); bb_y0 = fminf(bb_y0, fyi); bb_y1 = fmaxf(bb_y1, fyi);
+        }
         // the 14 fields of this step: lanes = 32 consecutive candidates -> one coalesced 256-byte store each
         double* p = sp + (size_t)i * sstride;
         if (st_xyt) {           // x, y, theta are re-read by the obstacle pass: keep them in L2
@@ -537,6 +544,50 @@ __device__ __forceinline__ FrxLaneOut frx_candidate(const FrxKernelArgs& A, cons
         const bool need_pred = OBS && costed && (cost_mask & (1u << FRX_COST_PREDICTION)) && A.O > 0;
         const bool need_d2o = XCOST && costed && (cost_mask & (1u << FRX_COST_DISTANCE_TO_OBSTACLES)) && A.n_obs_pos > 0;
         const bool need_col = OBS && candidate && A.check_collisions && (A.O > 0 || A.B > 0);
+        // ---- static boxes (road boundary): the warp culls them ONCE per tile against the bounding box of all positions
+        // of its candidates, lane b testing box b (fp32, inflated like frx_cull_radius); the boxes that can be reached go
+        // into a per-warp list the step loop walks instead of all A.B of them -- a lanelet network has hundreds of
+        // boundary segments, a tile of neighbouring candidates comes near a dozen
+        int n_near = -1;                                  // -1: no list, walk all boxes
+        if (OBS && A.B > 0 && A.B <= FRX_WALL_LIST && wall_list != nullptr && !A.defer_obs && __any_sync(pass, need_col)) {
+            const int kx0 = __reduce_min_sync(pass, need_col ? frx_f32_key(bb_x0) : 0x7fffffff);
+            const int kx1 = __reduce_max_sync(pass, need_col ? frx_f32_key(bb_x1) : (int)0x80000000);
+            const int ky0 = __reduce_min_sync(pass, need_col ? frx_f32_key(bb_y0) : 0x7fffffff);
+            const int ky1 = __reduce_max_sync(pass, need_col ? frx_f32_key(bb_y1) : (int)0x80000000);
+            const float x0 = frx_key_f32(kx0), x1 = frx_key_f32(kx1), y0 = frx_key_f32(ky0), y1 = frx_key_f32(ky1);
+            // an ego hull spans two consecutive positions of the box: it stays within sqrt(2) (rear-axle offset + half
+            // diagonal + half the largest step) of them, and a step is no longer than the box diagonal
+            const float diag = sqrtf((x1 - x0) * (x1 - x0) + (y1 - y0) * (y1 - y0));
+            const float grow = 1.4143f * ((float)A.wb_rear + sqrtf((float)(A.half_len * A.half_len + A.half_wid * A.half_wid)) + 0.5f * diag) *
+                               (1.f + 1e-5f) + 1e-6f * (fabsf(x0) + fabsf(x1) + fabsf(y0) + fabsf(y1)) + 1e-3f;
+            const float mx = 0.5f * (x0 + x1), my = 0.5f * (y0 + y1), hx = 0.5f * (x1 - x0) + grow, hy = 0.5f * (y1 - y0) + grow;
+            const bool finite = (fabsf(x0) + fabsf(x1) + fabsf(y0) + fabsf(y1)) < 3e38f;
+            int cnt = 0;
+            __syncwarp(pass);
+            for (int b0 = 0; b0 < A.B; b0 += 32) {
+                bool near = false;
+                if (b0 + lane < A.B) {
+                    const float4 c = __ldg(A.sobb32 + b0 + lane);
+                    near = !finite || ((fabsf(c.x - mx) <= hx + c.z) && (fabsf(c.y - my) <= hy + c.z));
+                }
+                // the lanes of `pass` are not always 0..31: every lane of the pass tests the boxes of its own index, the
+                // boxes of the absent lanes are kept unconditionally
+                const unsigned wm = __ballot_sync(pass, near) | (~pass & (b0 + 32 <= A.B ? 0xffffffffu : ((1u << (A.B - b0)) - 1u)));
+                if ((wm >> lane) & 1u) wall_list[cnt + __popc(wm & ((1u << lane) - 1u))] = (unsigned short)(b0 + lane);
+                // slots of absent lanes are written by the first lane of the pass
+                if (lane == __ffs(pass) - 1) {
+                    unsigned missing = wm & ~pass;
+                    while (missing) {
+                        const int l2 = __ffs(missing) - 1;
+                        missing &= missing - 1;
+                        wall_list[cnt + __popc(wm & ((1u << l2) - 1u))] = (unsigned short)(b0 + l2);
+                    }
+                }
+                cnt += __popc(wm);
+            }
+            __syncwarp(pass);
+            n_near = cnt;
+        }
         if ((need_pred || need_d2o || need_col) && !A.defer_obs) {      // deferred: frx_obstacle_kernel does this pass
             double pbx = 0, pby = 0, pux = 0, puy = 0;   // ego box of the previous step
             if (SEG > 1 && need_col && i0 >= 1 && i0 < i1) {      // ... which another lane wrote for a later segment
@@ -607,7 +658,9 @@ __device__ __forceinline__ FrxLaneOut frx_candidate(const FrxKernelArgs& A, cons
                             }
                         }
                         if (!boundary) {
-                            for (int b = 0; b < A.B; ++b) {
+                            const int nb = (n_near >= 0) ? n_near : A.B;
+                            for (int q2 = 0; q2 < nb; ++q2) {
+                                const int b = (n_near >= 0) ? (int)wall_list[q2] : q2;
                                 const double* __restrict__ sb = A.sobb + b * 8;
                                 double rr = er + __ldg(sb + 6);
                                 double ddx = __ldg(sb) - e.cx, ddy = __ldg(sb + 1) - e.cy;
@@ -751,6 +804,7 @@ __device__ __forceinline__ void frx_tile_body(const FrxKernelArgs& A, const int 
     for (int k = threadIdx.x; k < FRX_MAX_T_VALUES; k += FRX_THREADS) s_Tlen[k] = (k < A.nT) ? A.Tlen[k] : 0;
     for (int k = threadIdx.x; k < T_ROWS * TP; k += FRX_THREADS) s_tp[k] = __ldg(A.tpow + k);     // visible after the barrier below
     if (lane < FRX_MEMO_SLOTS) s_hdr[wib * FRX_MEMO_SLOTS + lane].valid = 0;
+    __shared__ unsigned short s_walls[OBS ? FRX_WARPS_PER_CTA * FRX_WALL_LIST : 1];     // per-warp list of reachable static boxes
     __shared__ unsigned int s_cnt[CNT_REASON1 + 10];     // per-CTA event counters
     __shared__ unsigned long long s_part[FRX_THREADS];   // last CTA: partial counter sums
     if (threadIdx.x < CNT_REASON1 + 10) s_cnt[threadIdx.x] = 0u;
@@ -878,7 +932,7 @@ __device__ __forceinline__ void frx_tile_body(const FrxKernelArgs& A, const int 
             if ((pass >> lane) & 1u) {
                 const int slot = ((mB >> lane) & 1u) ? sb : sa;
                 o = frx_candidate<SEG, OBS, XCOST>(A, cost_mask, pass, r, T, d0, dd0, ddd0, d1, dd1, ddd1, memo + (size_t)slot * M_FIELDS * MP,
-                                              hdr + slot, s_tp);
+                                              hdr + slot, s_tp, OBS ? s_walls + wib * FRX_WALL_LIST : nullptr);
             }
             __syncwarp();
             FRX_STAMP(4);                                                    // candidates of the pass evaluated
@@ -977,6 +1031,7 @@ __device__ __forceinline__ void frx_tile_body(const FrxKernelArgs& A, const int 
                 if (o.idx >= 0 && (b.idx < 0 || o.cost < b.cost || (o.cost == b.cost && o.idx < b.idx))) b = o;
             }
             s_best[0] = b;                          // local row, for the state copy below
+            FRX_PUBLISH_WINNER_SCALARS(A, b.idx);
             if (b.idx >= 0) b.idx += A.row_base;   // the winner record carries the GLOBAL row index
             *A.winner = b;
             A.host_res->winner = b;

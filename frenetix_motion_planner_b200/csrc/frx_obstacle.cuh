@@ -31,11 +31,6 @@
 #endif
 #define FRX_OBS_NOHIT 127u
 
-__device__ __forceinline__ int frx_f32_key(float f) {          // order-preserving float -> int
-    const int b = __float_as_int(f);
-    return b >= 0 ? b : (b ^ 0x7fffffff);
-}
-__device__ __forceinline__ float frx_key_f32(int k) { return __int_as_float(k >= 0 ? k : (k ^ 0x7fffffff)); }
 
 struct FrxObsAcc {      // what a thread carries to the end of the kernel
     double best_cost;
@@ -150,6 +145,7 @@ __device__ __forceinline__ void frx_obs_block_finish(const FrxKernelArgs& A, Frx
             if (o.idx >= 0 && (b.idx < 0 || o.cost < b.cost || (o.cost == b.cost && o.idx < b.idx))) b = o;
         }
         s_best[0] = b;
+        FRX_PUBLISH_WINNER_SCALARS(A, b.idx);
         if (b.idx >= 0) b.idx += A.row_base;   // the winner record carries the GLOBAL row index
         *A.winner = b;
         A.host_res->winner = b;

@@ -498,31 +498,50 @@ class ReactivePlannerB200:
     # output conversion (planner.py:394-515) without commonroad-io
     # ------------------------------------------------------------------------------------------
     def _compute_trajectory_pair(self, trajectory: TrajectorySample) -> tuple:
+        """planner.py:394-447: (Cartesian trajectory, curvilinear trajectory, lon samples, lat samples) of the selected
+        candidate.  Same values as the reference's per-state loop; the arithmetic is done on whole arrays first and the
+        state objects are filled from plain Python floats (the loop itself was most of a small plan's host time)."""
         c, cl = trajectory.cartesian, trajectory.curvilinear
         t0 = getattr(self.x_0, "time_step", 0)
-        wheelbase = _get(self.vehicle_params, "wheelbase")
-        cart_list, cl_list, lon_list, lat_list = [], [], [], []
-        for i in range(len(c.x)):
-            yaw = (c.theta[i] - c.theta[i - 1]) / self.dT if i > 0 else getattr(self.x_0, "yaw_rate", 0.0)
-            cart_list.append(PlannerState(time_step=t0 + i, position=np.array([c.x[i], c.y[i]]), orientation=c.theta[i],
-                                          velocity=c.v[i], acceleration=c.a[i], yaw_rate=yaw,
-                                          steering_angle=np.arctan2(wheelbase * c.kappa[i], 1.0)))
-            cl_list.append(SimpleNamespace(time_step=t0 + i, position=np.array([cl.s[i], cl.d[i]]), velocity=c.v[i],
-                                           acceleration=c.a[i], orientation=c.theta[i], yaw_rate=c.kappa[i]))
-            lon_list.append([cl.s[i], cl.s_dot[i], cl.s_ddot[i]])
-            lat_list.append([cl.d[i], cl.d_dot[i], cl.d_ddot[i]])
-        cart = _Trajectory(initial_time_step=t0, state_list=cart_list)
-        lo, hi = self.x_0.orientation - np.pi, self.x_0.orientation + np.pi      # shift_orientation, planner.py:536-542
-        for st in cart.state_list:
-            while st.orientation < lo:
-                st.orientation += 2 * np.pi
-            while st.orientation > hi:
-                st.orientation -= 2 * np.pi
-        return cart, _Trajectory(initial_time_step=t0, state_list=cl_list), lon_list, lat_list
+        theta = np.asarray(c.theta, dtype=np.float64)
+        n = theta.size
+        yaw = np.empty(n)
+        yaw[0] = getattr(self.x_0, "yaw_rate", 0.0)
+        yaw[1:] = (theta[1:] - theta[:-1]) / self.dT
+        steer = np.arctan2(_get(self.vehicle_params, "wheelbase") * np.asarray(c.kappa, dtype=np.float64), 1.0)
+        # shift_orientation (planner.py:536-542) into [x_0.orientation - pi, x_0.orientation + pi]; almost always a no-op
+        lo, hi = self.x_0.orientation - np.pi, self.x_0.orientation + np.pi
+        th = theta.tolist()
+        if theta.min() < lo or theta.max() > hi:
+            for i, o in enumerate(th):
+                while o < lo:
+                    o += 2 * np.pi
+                while o > hi:
+                    o -= 2 * np.pi
+                th[i] = o
+        pos = np.stack([np.asarray(c.x, dtype=np.float64), np.asarray(c.y, dtype=np.float64)], axis=1)
+        pos_cl = np.stack([np.asarray(cl.s, dtype=np.float64), np.asarray(cl.d, dtype=np.float64)], axis=1)
+        v, a, kap = np.asarray(c.v).tolist(), np.asarray(c.a).tolist(), np.asarray(c.kappa).tolist()
+        yaw_l, steer_l, th_raw = yaw.tolist(), steer.tolist(), theta.tolist()
+        cart_list = [PlannerState(time_step=t0 + i, position=pos[i], orientation=th[i], velocity=v[i], acceleration=a[i],
+                                  yaw_rate=yaw_l[i], steering_angle=steer_l[i]) for i in range(n)]
+        cl_list = [SimpleNamespace(time_step=t0 + i, position=pos_cl[i], velocity=v[i], acceleration=a[i], orientation=th_raw[i],
+                                   yaw_rate=kap[i]) for i in range(n)]
+        lon_list = np.stack([cl.s, cl.s_dot, cl.s_ddot], axis=1).tolist()
+        lat_list = np.stack([cl.d, cl.d_dot, cl.d_ddot], axis=1).tolist()
+        return (_Trajectory(initial_time_step=t0, state_list=cart_list), _Trajectory(initial_time_step=t0, state_list=cl_list),
+                lon_list, lat_list)
 
     def convert_state_list_to_commonroad_object(self, state_list, obstacle_id: int = 42):
+        """planner.py:488-515: the ego as a dynamic obstacle whose positions are shifted from the rear axle to the centre."""
         wb_rear = _get(self.vehicle_params, "wb_rear_axle")
-        shifted = [s.shift_positions_to_center(wb_rear) for s in state_list]
+        ori = np.array([s.orientation for s in state_list], dtype=np.float64)
+        pos = np.array([s.position for s in state_list], dtype=np.float64) + wb_rear * np.stack([np.cos(ori), np.sin(ori)], axis=1)
+        shifted = []
+        for k, s in enumerate(state_list):
+            c = PlannerState(**s.__dict__)
+            c.position = pos[k]
+            shifted.append(c)
         return SimpleNamespace(obstacle_id=obstacle_id, initial_state=shifted[0],
                                obstacle_shape=SimpleNamespace(length=_get(self.vehicle_params, "length"),
                                                               width=_get(self.vehicle_params, "width")),

@@ -116,8 +116,14 @@ class TrajectorySample:
         if self._own is None:
             self._fetch()
             b, r = self._b, self._row
-            self._own = (int(b.flags[r]), float(b.total[r]), np.array(b.costs[r], dtype=np.float64), int(b.traj_len[r]),
-                         b.sampling_row(r))
+            if b.winner_row is not None and r == b.winner_row and b._flags is None and hasattr(b._h, "winner_record"):
+                # the selected candidate's scalars came back with the arg-min: no read-back of whole arrays for one row
+                b._live()
+                fl, tl, tot, costs = b._h.winner_record()
+                self._own = (fl, tot, np.array(costs, dtype=np.float64), tl, b.sampling_row(r))
+            else:
+                self._own = (int(b.flags[r]), float(b.total[r]), np.array(b.costs[r], dtype=np.float64), int(b.traj_len[r]),
+                             b.sampling_row(r))
         return self
 
     # ---- scalars --------------------------------------------------------------------------

@@ -212,6 +212,8 @@ int frx_get_flags(frx_ctx* ctx, int64_t first, int64_t count, uint32_t* flags, i
  * host-side copy -- no device round trip (reference: the optimal trajectory handed back by plan(),
  * frenetix_motion_planner/reactive_planner.py:89-94) */
 int frx_winner_states(frx_ctx* ctx, uint32_t field_mask, double* out);
+/* ... and its scalars from the same record: flags, traj_len, total cost, the n_costs unweighted cost terms */
+int frx_winner_record(frx_ctx* ctx, uint32_t* flags, int32_t* traj_len, double* total, double* costs);
 /* raw device pointers of the last plan for zero-copy consumers: states [ceil(N / 32)][Nt][14][32] (element (field f,
  * step i) of candidate r at (((r / 32) * Nt + i) * 14 + f) * 32 + r % 32), costs [N][n_costs], total [N], flags [N] */
 int frx_device_pointers(frx_ctx* ctx, void** states, void** costs, void** total, void** flags);

@@ -117,6 +117,10 @@ class OracleHandler:
         w = self._out["argmin"]
         return self.get_states(np.array([w]), fields)[:, 0, :]
 
+    def winner_record(self):
+        w = self._out["argmin"]
+        return int(self._out["flags"][w]), int(self._out["traj_len"][w]), float(self._out["total"][w]), self._out["costs"][w].copy()
+
     def close(self):
         pass
 

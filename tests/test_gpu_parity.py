@@ -87,6 +87,10 @@ def test_winner_states_record_equals_gathered_row(name):
     assert w.shape == ref_rows.shape
     assert np.array_equal(w, ref_rows)
     assert np.array_equal(w, dev["states"][:, dev["argmin"], :])
+    fl, tl, tot, costs = h.winner_record()                      # the winner's scalars travel in the same record
+    a = dev["argmin"]
+    assert (fl, tl, tot) == (int(dev["flags"][a]), int(dev["traj_len"][a]), float(dev["total"][a]))
+    assert np.array_equal(costs, dev["costs"][a])
 
 
 def test_pinned_host_matrix_is_read_in_place():
@@ -188,3 +192,36 @@ def test_cpp_flavour_switches_match_the_oracle(name):
     assert not np.array_equal(base["flags"] & fo.FLAG_FEASIBLE, ora["flags"] & fo.FLAG_FEASIBLE)
     k = list(ora["cost_names"]).index("velocity_offset")
     assert not np.allclose(base["costs"][:, k], ora["costs"][:, k])
+
+
+@pytest.mark.parametrize("seg", [1, 2, 4])
+@pytest.mark.parametrize("name", ["tjunction_draw", "arc_hv_draw_pred"])
+def test_static_boxes_fused_pass_tile_cull_equals_oracle(name, seg, monkeypatch):
+    """Road-boundary boxes in the FUSED pass (small plans, every SEG instance): the per-tile cull list must select what
+    testing every box selects -- against the oracle, which tests every box, with the T-junction network's 82 walls, with more
+    boxes than one 32-lane round, with a box list longer than the cull list (falls back to the linear scan) and with walls
+    far away (empty list)."""
+    import json
+    import os
+    from helpers import GOLDEN_DIR
+    from frenetix_motion_planner_b200.road_boundary import road_boundary_obbs
+    monkeypatch.setenv("FRX_SEG", str(seg))
+    monkeypatch.setenv("FRX_SPLIT_OBS", "0")
+    g, ref, prm, preds = load_golden(name)
+    S = g["sampling"]
+    raw = json.load(open(os.path.join(GOLDEN_DIR, "tjunction_lanelets.json")))
+    net = {int(k): dict(left=np.array(v["left"]), right=np.array(v["right"]), adj_left=v["adj_left"], adj_right=v["adj_right"])
+           for k, v in raw.items()}
+    walls = road_boundary_obbs(net)
+    if not name.startswith("tjunction"):          # move the network onto this case's reference path
+        walls = walls.copy()
+        walls[:, 0] += ref.ref_x[30] - walls[:, 0].mean(); walls[:, 1] += ref.ref_y[30] - walls[:, 1].mean()
+    rng = np.random.default_rng(3)
+    far = np.column_stack([rng.uniform(4000, 5000, 40), rng.uniform(4000, 5000, 40), rng.uniform(-3, 3, 40), rng.uniform(1, 9, 40),
+                           rng.uniform(0.05, 1, 40)])
+    many = np.vstack([walls] * 7)[:600]                                          # > FRX_WALL_LIST boxes
+    for boxes in (walls, np.vstack([far, walls[:45]]), far, many):
+        ora = fo.plan(S, ref, prm, preds, static_obbs=boxes)
+        dev = device_plan(S, ref, prm, preds, static_obbs=boxes)
+        compare_with_oracle(dev, ora, prm)
+    assert (fo.plan(S, ref, prm, preds, static_obbs=walls)["flags"] & fo.FLAG_BOUNDARY).any()
