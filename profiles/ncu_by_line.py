@@ -16,7 +16,7 @@ src_csv, dis, sym = sys.argv[1:4]
 top_n = int(sys.argv[4]) if len(sys.argv) > 4 else 40
 body_lo = int(sys.argv[5]) if len(sys.argv) > 5 else 0
 body_hi = int(sys.argv[6]) if len(sys.argv) > 6 else 10 ** 9
-KERNEL_FILES = ("frx_eval_tile.cuh", "frx_kernels.cu")   # attribution preference: body first, helpers second
+KERNEL_FILES = ("frx_eval_tile.cuh", "frx_obstacle.cuh", "frx_kernels.cu", "frx_reference.cuh")   # attribution preference: bodies first, helpers second
 
 off2 = {}
 chain = []
@@ -43,7 +43,7 @@ for l in open(dis):
         body = None
         for kf in KERNEL_FILES:
             for f, ln in chain:
-                if f == kf and (kf != KERNEL_FILES[0] or body_lo <= ln <= body_hi):
+                if f == kf and (kf not in KERNEL_FILES[:2] or body_lo <= ln <= body_hi):
                     body = (kf, ln)
                     break
             if body is not None:
