@@ -900,9 +900,13 @@ int frx_set_exchange(frx_ctx* ctx, void* page, int32_t rank, int32_t world) {
     ctx->xchg_host = ctx->xchg_dev = nullptr; ctx->xchg_epoch = 0;
     if (!page) return FRX_OK;
     REQUIRE(world >= 1 && world <= FRX_XCHG_MAX_RANKS && rank >= 0 && rank < world, "frx_set_exchange: bad rank / world size");
-    cudaError_t e = cudaHostRegister(page, FRX_XCHG_PAGE_BYTES, cudaHostRegisterMapped | cudaHostRegisterPortable);
-    if (e == cudaErrorHostMemoryAlreadyRegistered) cudaGetLastError();      // another context of this process did it
-    else { CK(e); ctx->xchg_registered = true; }
+    cudaPointerAttributes at;
+    const bool known = cudaPointerGetAttributes(&at, page) == cudaSuccess && at.type == cudaMemoryTypeHost;
+    if (!known) {                        // (another context of this process may have registered the page already)
+        cudaGetLastError();
+        CK(cudaHostRegister(page, FRX_XCHG_PAGE_BYTES, cudaHostRegisterMapped | cudaHostRegisterPortable));
+        ctx->xchg_registered = true;
+    }
     void* d = nullptr;
     CK(cudaHostGetDevicePointer(&d, page, 0));
     ctx->xchg_host = (FrxXchgSlot*)page; ctx->xchg_dev = (FrxXchgSlot*)d;

@@ -113,6 +113,9 @@ class Params:
     v_delta_max: float = 0.4
     # CalculateVelocityOffsetCost(..., norm_order=2): squared instead of absolute offsets
     velocity_offset_norm: int = 1
+    # prediction cost: 0 = inverse Mahalanobis (python path), 1 = CalculateCollisionProbabilityFast, i.e. the in-tree
+    # get_collision_probability_fast (risk_assessment/collision_probability.py:141-261; prediction_costs :344-348)
+    prediction_cost_mode: int = 0
 
     def active_costs(self):
         names = [k for k, w in self.cost_weights.items() if w != 0]
@@ -294,6 +297,141 @@ def simps(y, dx):
     return result
 
 
+# ----------------------------------------------------------------------------------------------
+# bivariate normal rectangle probability: what scipy.stats.mvn.mvnun(lower, upper, mean, cov) returns for
+# two dimensions (Genz's MVNDST calls the deterministic bivariate routine there).  scipy removed the
+# module; this is Genz's BVND algorithm (A. Genz, "Numerical computation of rectangular bivariate and
+# trivariate normal and t probabilities", Statistics and Computing 14, 2004): Gauss-Legendre quadrature of
+# the Plackett integral with 6 / 12 / 20 points depending on |rho|, the |rho| > 0.925 branch with its
+# asymptotic corrections.  Checked against scipy.stats.multivariate_normal.cdf(..., lower_limit=...)
+# to 4e-16 (tests/test_oracle_golden.py).
+# ----------------------------------------------------------------------------------------------
+_GL_W = {3: [0.1713244923791705, 0.3607615730481384, 0.4679139345726904],
+         6: [0.04717533638651177, 0.1069393259953183, 0.1600783285433464, 0.2031674267230659, 0.2334925365383547,
+             0.2491470458134029],
+         10: [0.01761400713915212, 0.04060142980038694, 0.06267204833410906, 0.08327674157670475, 0.1019301198172404,
+              0.1181945319615184, 0.1316886384491766, 0.1420961093183821, 0.1491729864726037, 0.1527533871307259]}
+_GL_X = {3: [0.9324695142031522, 0.6612093864662647, 0.2386191860831970],
+         6: [0.9815606342467191, 0.9041172563704750, 0.7699026741943050, 0.5873179542866171, 0.3678314989981802,
+             0.1252334085114692],
+         10: [0.9931285991850949, 0.9639719272779138, 0.9122344282513259, 0.8391169718222188, 0.7463319064601508,
+              0.6360536807265150, 0.5108670019508271, 0.3737060887154196, 0.2277858511416451, 0.07652652113349733]}
+
+
+def _phid(z):
+    return 0.5 * math.erfc(-z / math.sqrt(2.0))
+
+
+def bvnu(dh, dk, r):
+    """P(X > dh, Y > dk), standard bivariate normal with correlation r."""
+    if r == 0:
+        return _phid(-dh) * _phid(-dk)
+    tp = 2 * math.pi
+    h, k = dh, dk
+    hk = h * k
+    bvn = 0.0
+    lg = 3 if abs(r) < 0.3 else (6 if abs(r) < 0.75 else 10)
+    w, x = _GL_W[lg], _GL_X[lg]
+    if abs(r) < 0.925:
+        hs = (h * h + k * k) / 2
+        asr = math.asin(r) / 2
+        for wi, xi in zip(w, x):
+            for xs in (1 - xi, 1 + xi):
+                sn = math.sin(asr * xs)
+                bvn += wi * math.exp((sn * hk - hs) / (1 - sn * sn))
+        bvn = bvn * asr / tp + _phid(-h) * _phid(-k)
+    else:
+        if r < 0:
+            k = -k
+            hk = -hk
+        if abs(r) < 1:
+            as_ = 1 - r * r
+            a = math.sqrt(as_)
+            bs = (h - k) ** 2
+            asr = -(bs / as_ + hk) / 2
+            c = (4 - hk) / 8
+            d = (12 - hk) / 80
+            if asr > -100:
+                bvn = a * math.exp(asr) * (1 - c * (bs - as_) * (1 - d * bs) / 3 + c * d * as_ * as_)
+            if hk > -100:
+                b = math.sqrt(bs)
+                sp = math.sqrt(tp) * _phid(-b / a)
+                bvn = bvn - math.exp(-hk / 2) * sp * b * (1 - c * bs * (1 - d * bs) / 3)
+            a = a / 2
+            acc = 0.0
+            for wi, xi in zip(w, x):
+                for xx in (1 - xi, 1 + xi):
+                    xs = (a * xx) ** 2
+                    asr = -(bs / xs + hk) / 2
+                    if asr > -100:
+                        sp = 1 + c * xs * (1 + 5 * d * xs)
+                        rs = math.sqrt(1 - xs)
+                        ep = math.exp(-(hk / 2) * xs / (1 + rs) ** 2) / rs
+                        acc += wi * math.exp(asr) * (sp - ep)
+            bvn = (a * acc - bvn) / tp
+        if r > 0:
+            bvn = bvn + _phid(-max(h, k))
+        elif h >= k:
+            bvn = -bvn
+        else:
+            L = _phid(k) - _phid(h) if h < 0 else _phid(-h) - _phid(-k)
+            bvn = L - bvn
+    return max(0.0, min(1.0, bvn))
+
+
+def mvnun2(lower, upper, mu, cov):
+    """Rectangle probability of N(mu, cov) in two dimensions (the value part of scipy.stats.mvn.mvnun)."""
+    sx, sy = math.sqrt(cov[0][0]), math.sqrt(cov[1][1])
+    r = cov[0][1] / (sx * sy)
+    a1, a2 = (lower[0] - mu[0]) / sx, (lower[1] - mu[1]) / sy
+    b1, b2 = (upper[0] - mu[0]) / sx, (upper[1] - mu[1]) / sy
+    return bvnu(a1, a2, r) - bvnu(b1, a2, r) - bvnu(a1, b2, r) + bvnu(b1, b2, r)
+
+
+def collision_probability_fast(x, y, theta, predictions, veh_length, veh_width):
+    """risk_assessment/collision_probability.py:141-261, restated: per obstacle the per-step probability that the ego
+    (three axis-aligned rectangles of length / 3 x width around the REAR-AXLE position and +- length / 3 along its heading,
+    :336-371) overlaps the obstacle (three normal distributions: predicted mean and the mean +- length / 2 along the NEXT
+    step's yaw, :173-178), zero when all three means are more than 5 m away."""
+    ego_pos = np.stack((x, y), axis=-1)
+    offset = np.array([veh_length / 6, veh_width / 2])
+    out = {}
+    for oid, pred in enumerate(predictions):
+        mean_list, cov_list, yaw_list = pred["pos_list"], pred["cov_list"], pred["orientation_list"]
+        length = pred["shape"]["length"]
+        probs = []
+        min_len = min(len(x), len(mean_list))
+        ego_pos_array = ego_pos[1:min_len]
+        dev = np.stack((np.cos(yaw_list[1:min_len]), np.sin(yaw_list[1:min_len])), axis=-1) * length / 2
+        mean_array = np.array(mean_list[:min_len - 1])
+        total_mean_array = np.array([mean_array, mean_array + dev, mean_array - dev])
+        dist = total_mean_array - ego_pos_array
+        dist = np.sqrt(dist[:, :, 0] ** 2 + dist[:, :, 1] ** 2)
+        far = dist.min(axis=0) > 5.0
+        for i in range(1, len(x)):
+            if i < len(mean_list):
+                if far[i - 1]:
+                    prob = 0.0
+                else:
+                    cov = cov_list[i - 1]
+                    if all(c == 0 for c in (cov[0][0], cov[0][1], cov[1][0], cov[1][1])):
+                        cov = [[0.1, 0.0], [0.0, 0.1]]
+                    prob = 0.0
+                    c0 = ego_pos_array[i - 1]
+                    ax = np.array([math.cos(theta[i]), math.sin(theta[i])])
+                    r_x = veh_length / 2
+                    centers = np.array([c0, c0 + r_x * (2 / 3) * ax, c0 - r_x * (2 / 3) * ax])
+                    upper, lower = centers + offset, centers - offset
+                    for mu in total_mean_array[:, i - 1]:
+                        for q in range(3):
+                            prob += mvnun2(lower[q], upper[q], mu, cov)
+            else:
+                prob = 0.0
+            probs.append(prob / 3)
+        out[oid] = np.array(probs)
+    return out
+
+
 def _costs_for(name, st, c_lon, c_lat, prm: Params, predictions, inv_covs, Nt):
     """partial_cost_functions.py -- one unweighted cost term for one candidate."""
     x, y = st[F_X], st[F_Y]
@@ -313,6 +451,12 @@ def _costs_for(name, st, c_lon, c_lat, prm: Params, predictions, inv_covs, Nt):
     if name == "distance_to_reference_path":         # :154-169 (len(d + 4) == len(d))
         d = st[F_D]
         return float((np.sum(np.abs(d)) + np.abs(d[-1]) * 5) / len(d + 4))
+    if name == "prediction" and prm.prediction_cost_mode == 1:
+        probs = collision_probability_fast(x, y, st[F_THETA], predictions, prm.length, prm.width)
+        pred_costs = 0
+        for key in probs:
+            pred_costs += np.sum(probs[key])
+        return pred_costs
     if name == "prediction":                         # :341-356 + collision_probability.py:264-299
         pred_costs = 0
         for o, pred in enumerate(predictions):

@@ -246,6 +246,71 @@ def refpath_cases():
     print("ref paths:", {k: v.shape for k, v in out.items() if k.endswith("_smooth")})
 
 
+def collision_probability_cases():
+    """get_collision_probability_fast of the reference (risk_assessment/collision_probability.py:141-261) on stored
+    trajectories -> ref_collision_probability.npz.  Two absent third-party calls are stood in for: scipy.stats.mvn.mvnun
+    (removed from scipy) by multivariate_normal.cdf(upper, lower_limit=lower), which evaluates the same rectangle
+    probability, and pycrcc.RectOBB (centre, half length, x axis) by a three-line class."""
+    import importlib
+    from scipy.stats import multivariate_normal
+    cp = importlib.import_module("risk_assessment.collision_probability")
+
+    class _Mvn:
+        @staticmethod
+        def mvnun(lower, upper, mu, cov):
+            return multivariate_normal.cdf(np.asarray(upper), mean=np.asarray(mu), cov=np.asarray(cov), lower_limit=np.asarray(lower)), 0
+
+    class _RectOBB:
+        def __init__(self, r_x, r_y, orientation, cx, cy):
+            self._r, self._o, self._c = r_x, orientation, np.array([cx, cy])
+
+        def center(self):
+            return self._c
+
+        def r_x(self):
+            return self._r
+
+        def local_x_axis(self):
+            return np.array([np.cos(self._o), np.sin(self._o)])
+    cp.mvn = _Mvn
+    cp.pycrcc = types.SimpleNamespace(RectOBB=_RectOBB)
+    veh = types.SimpleNamespace(**syn.VEHICLE_2)
+    out = {}
+    n_case = 0
+    for name in ("arc_hv_draw_pred", "tjunction_draw", "scurve_lowvel_draw"):
+        g = np.load(os.path.join(HERE, f"ref_{name}.npz"))
+        rows = np.flatnonzero(g["stored"])[::37][:6]
+        for variant in range(2):
+            preds = {}
+            for o in range(int(g["n_obs"])):
+                cov = g[f"pred{o}_cov"].copy()
+                pos = g[f"pred{o}_pos"].copy()
+                if variant == 1:                      # correlated covariances, a zero matrix, obstacles pulled next to the ego
+                    for k in range(cov.shape[0]):
+                        r = [0.5, -0.8, 0.95, -0.97, 0.2][(k + o) % 5]
+                        sx, sy = 0.3 + 0.02 * k, 0.5 + 0.01 * k
+                        cov[k] = [[sx * sx, r * sx * sy], [r * sx * sy, sy * sy]]
+                    cov[3] = 0.0
+                    pos = pos + (np.array([g["states"][0, rows[0], 5], g["states"][1, rows[0], 5]]) - pos[4]) * 0.9
+                preds[100 + o] = {"pos_list": pos, "cov_list": cov, "orientation_list": g[f"pred{o}_ori"],
+                                  "shape": {"length": float(g[f"pred{o}_shape"][0]), "width": float(g[f"pred{o}_shape"][1])}}
+            for r in rows:
+                traj = types.SimpleNamespace(cartesian=types.SimpleNamespace(x=g["states"][0, r], y=g["states"][1, r], theta=g["states"][2, r]))
+                probs = cp.get_collision_probability_fast(traj, preds, veh)
+                key = f"c{n_case}"
+                out[key + "_xyt"] = np.stack([g["states"][0, r], g["states"][1, r], g["states"][2, r]])
+                out[key + "_n_obs"] = len(preds)
+                for o, oid in enumerate(preds):
+                    out[f"{key}_o{o}_pos"], out[f"{key}_o{o}_cov"] = preds[oid]["pos_list"], preds[oid]["cov_list"]
+                    out[f"{key}_o{o}_ori"], out[f"{key}_o{o}_shape"] = preds[oid]["orientation_list"], g[f"pred{o}_shape"]
+                    out[f"{key}_o{o}_probs"] = probs[oid]
+                n_case += 1
+    out["n_cases"] = n_case
+    np.savez_compressed(os.path.join(HERE, "ref_collision_probability.npz"), **out)
+    nz = sum(int((out[k] > 0).sum()) for k in out if k.endswith("_probs"))
+    print("collision probability cases:", n_case, "non-zero step probabilities:", nz)
+
+
 def sampling_order_cases():
     """Iteration order of the reference's level SETS (python hash order: it fixes uniqueId = row index and every
     equal-cost tie) for random v / d intervals, all levels, plus the cpp path's unions -> ref_sampling_order.npz."""
@@ -382,6 +447,7 @@ if __name__ == "__main__":
         initial_state_cases()
         sampling_order_cases()
         refpath_cases()
+        collision_probability_cases()
         sys.exit(0)
     if "--tjunction" in sys.argv:
         poly, x_cl, x_0, preds = tjunction_inputs()
@@ -417,3 +483,4 @@ if __name__ == "__main__":
     initial_state_cases()
     sampling_order_cases()
     refpath_cases()
+    collision_probability_cases()
