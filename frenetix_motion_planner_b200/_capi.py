@@ -55,7 +55,8 @@ class FrxParams(C.Structure):
                 ("n_costs", C.c_int32), ("cost_ids", C.c_int32 * FRX_MAX_COSTS),
                 ("cost_weights", C.c_double * FRX_MAX_COSTS),
                 ("store_states", C.c_int32), ("check_collisions", C.c_int32),
-                ("curvature_rate_from_v_delta", C.c_int32), ("velocity_offset_norm", C.c_int32), ("v_delta_max", C.c_double)]
+                ("curvature_rate_from_v_delta", C.c_int32), ("velocity_offset_norm", C.c_int32), ("v_delta_max", C.c_double),
+                ("prediction_cost_mode", C.c_int32), ("reserved_", C.c_int32)]
 
 
 class FrxResult(C.Structure):
@@ -209,7 +210,8 @@ class Handler:
     def set_params(self, *, dt, N, low_vel_mode, draw_traj_set, kinematic_debug, a_max, v_switch, delta_max,
                    wheelbase, wb_rear_axle, length, width, x0_orientation, desired_velocity,
                    cost_names: Sequence[str], cost_weights: Sequence[float], store_states=True,
-                   check_collisions=True, curvature_rate_from_v_delta=False, v_delta_max=0.4, velocity_offset_norm=1):
+                   check_collisions=True, curvature_rate_from_v_delta=False, v_delta_max=0.4, velocity_offset_norm=1,
+                   prediction_cost_mode=0):
         p = FrxParams()
         p.dt, p.N = float(dt), int(N)
         p.low_vel_mode, p.draw_traj_set, p.kinematic_debug = int(bool(low_vel_mode)), int(bool(draw_traj_set)), int(bool(kinematic_debug))
@@ -228,6 +230,7 @@ class Handler:
         p.store_states, p.check_collisions = int(bool(store_states)), int(bool(check_collisions))
         p.curvature_rate_from_v_delta, p.v_delta_max = int(bool(curvature_rate_from_v_delta)), float(v_delta_max)
         p.velocity_offset_norm = int(velocity_offset_norm)
+        p.prediction_cost_mode = int(prediction_cost_mode)
         self._check(self._lib.frx_set_params(self._ctx, C.byref(p)))
         self.n_costs = p.n_costs
         self.Nt = int(N) + 1

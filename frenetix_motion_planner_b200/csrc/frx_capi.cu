@@ -27,6 +27,8 @@ void frx_launch_static_prep(int B, const double* obb, double* out, cudaStream_t 
 void frx_launch_obstacle_compact(int O, int Tp, int Nt, const double* obs, const int* obs_len, double ox, double oy, double* pred,
                                  double* hull, float4* hull32, int* n_pred, int* n_hull, cudaStream_t st);
 void frx_launch_static_cull(int B, const double* sobb, double ox, double oy, float4* out, cudaStream_t st);
+void frx_launch_prob_records(int O, int T, int Tp, const double* pos, const double* cov, const double* theta, const double* hl,
+                             const int* obs_len, double* out, cudaStream_t st);
 double frx_measure_fp64_peak(int sm_count, cudaStream_t st, cudaError_t* err);
 void frx_launch_reference_tables(int M, int Mpad, const double* xy, double* tab, double* scratch, cudaStream_t st);
 void frx_launch_initial_state(int M, int Mpad, const double* tab, const double* in, double wheelbase, int low, double* out,
@@ -80,6 +82,7 @@ struct frx_ctx {
 
     DevBuf<double> ref; int M = 0, Mpad = 0; double inv_step = 0.0;
     DevBuf<double> Ttab; DevBuf<int> Tlen; DevBuf<double> tpow; int nT = 0, tpitch = 0;
+    DevBuf<double> oprob; bool prob_ready = false;
     DevBuf<double> opred, ohull; DevBuf<float4> ohull32, sobb32; DevBuf<int> on_pred, on_hull; int compact_Nt = 0;
     double origin_x = 0.0, origin_y = 0.0;     // frame of the fp32 cull records: first vertex of the reference path
     bool sobb32_dirty = true;
@@ -170,7 +173,7 @@ int frx_destroy(frx_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
     ctx->ref.release(); ctx->Ttab.release(); ctx->Tlen.release(); ctx->tpow.release();
-    ctx->opred.release(); ctx->ohull.release(); ctx->ohull32.release(); ctx->sobb32.release(); ctx->on_pred.release(); ctx->on_hull.release();
+    ctx->oprob.release(); ctx->opred.release(); ctx->ohull.release(); ctx->ohull32.release(); ctx->sobb32.release(); ctx->on_pred.release(); ctx->on_hull.release();
     ctx->obs.release(); ctx->raw_pos.release(); ctx->raw_cov.release(); ctx->raw_theta.release();
     ctx->raw_hl.release(); ctx->raw_hw.release(); ctx->obs_len.release(); ctx->obs_pos.release();
     ctx->sobb.release(); ctx->raw_sobb.release(); ctx->sampling.release(); ctx->grid.release();
@@ -288,6 +291,7 @@ int frx_set_params(frx_ctx* ctx, const frx_params* p) {
         REQUIRE(p->cost_ids[k] >= 0 && p->cost_ids[k] < FRX_NUM_COST_TERMS, "frx_set_params: unknown cost id");
     REQUIRE(!p->curvature_rate_from_v_delta || p->v_delta_max > 0, "frx_set_params: v_delta_max must be > 0");
     REQUIRE(p->velocity_offset_norm >= 0 && p->velocity_offset_norm <= 2, "frx_set_params: velocity_offset_norm must be 0, 1 or 2");
+    REQUIRE(p->prediction_cost_mode == 0 || p->prediction_cost_mode == 1, "frx_set_params: prediction_cost_mode must be 0 or 1");
     if (ctx->have_params && ctx->prm.N != p->N) ctx->have_tables = false;
     ctx->prm = *p;
     ctx->kappa_max = tan(p->delta_max) / p->wheelbase;   // reactive_planner.py:492
@@ -348,7 +352,7 @@ int frx_set_predictions(frx_ctx* ctx, int32_t O, int32_t T, const double* pos, c
     CK(cudaStreamSynchronize(st));   // host buffers may be pageable and reused by the caller
     // the SoA table (inverse covariances, hulls) is built at plan time, when the step pitch (32 x chunks of the
     // planning horizon) is known
-    ctx->O = O; ctx->T = T; ctx->Tp = 0;
+    ctx->O = O; ctx->T = T; ctx->Tp = 0; ctx->prob_ready = false;
     return FRX_OK;
 }
 
@@ -422,6 +426,14 @@ static int prepare_plan(frx_ctx* ctx, long long N, const double* d_sampling, boo
                                     ctx->ohull.p, ctx->ohull32.p, ctx->on_pred.p, ctx->on_hull.p, st);
         CK(cudaGetLastError());
         ctx->compact_Nt = Nt;
+        ctx->prob_ready = false;
+    }
+    if (ctx->O > 0 && p.prediction_cost_mode == 1 && !ctx->prob_ready) {
+        CK(ctx->oprob.reserve((size_t)ctx->Tp * ctx->O * 8));
+        frx_launch_prob_records(ctx->O, ctx->T, ctx->Tp, ctx->raw_pos.p, ctx->raw_cov.p, ctx->raw_theta.p, ctx->raw_hl.p,
+                                ctx->obs_len.p, ctx->oprob.p, st);
+        CK(cudaGetLastError());
+        ctx->prob_ready = true;
     }
     if (ctx->B > 0 && ctx->sobb32_dirty) {
         CK(ctx->sobb32.reserve((size_t)ctx->B));
@@ -456,6 +468,7 @@ static int prepare_plan(frx_ctx* ctx, long long N, const double* d_sampling, boo
     a.mpitch = frx_memo_pitch_host(Nt);
     a.obs = ctx->obs.p; a.obs_len = ctx->obs_len.p; a.O = ctx->O; a.Tp = ctx->Tp;
     a.opred = ctx->opred.p; a.ohull = ctx->ohull.p; a.on_pred = ctx->on_pred.p; a.on_hull = ctx->on_hull.p;
+    a.oprob = ctx->oprob.p; a.pred_mode = (p.prediction_cost_mode == 1) ? 1 : 0;
     a.ohull32 = ctx->ohull32.p; a.sobb32 = ctx->sobb32.p; a.origin_x = ctx->origin_x; a.origin_y = ctx->origin_y;
     a.obs_pos = ctx->obs_pos.p; a.n_obs_pos = ctx->n_obs_pos; a.sobb = ctx->sobb.p; a.B = ctx->B;
     a.sampling = grid_mode ? nullptr : d_sampling;
@@ -524,6 +537,7 @@ static int choose_obstacle_split(frx_ctx* ctx, FrxKernelArgs* a, int grid) {
     for (int k = 0; k < a->n_costs; ++k) d2o |= (a->cost_ids[k] == FRX_COST_DISTANCE_TO_OBSTACLES) && a->n_obs_pos > 0;
     bool split = (obs || d2o) && a->seg == 1;
     if (const char* e = getenv("FRX_SPLIT_OBS")) split = (obs || d2o) && e[0] == '1';
+    if (obs && a->pred_mode == 1) split = true;      // the collision-probability cost only exists in frx_obstacle_kernel<1>
     a->defer_obs = split ? 1 : 0;
     if (split) {
         const size_t need = (size_t)frx_obstacle_pass_max_grid(ctx->sm_count);
@@ -697,6 +711,7 @@ int frx_plan_batched(int32_t n_agents, frx_ctx** ctxs, const int64_t* n_rows, co
     int nchunk0 = -1, max_Mpad = 0, occ = 1;
     for (int a = 0; a < n_agents; ++a) {
         REQUIRE(ctxs[a] && ctxs[a]->device == ctx->device, "frx_plan_batched: all contexts must live on one device");
+        REQUIRE(ctxs[a]->prm.prediction_cost_mode == 0, "frx_plan_batched: prediction_cost_mode 1 is not available in the batched launch");
         REQUIRE(n_rows[a] >= 1 && samplings[a], "frx_plan_batched: empty sampling matrix");
         total_rows += n_rows[a];
     }

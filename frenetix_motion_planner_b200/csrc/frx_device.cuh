@@ -115,6 +115,8 @@ struct FrxKernelArgs {
     const double* opred;    // [Tp][O][6] per-step compact prediction records (frx_obstacle_compact_kernel): px, py, iv00,
                             //            iv01 + iv10, iv11, 0 -- the quadratic form of the inverse covariance
     const double* ohull;    // [Tp][O][8] per-step compact hull records
+    const double* oprob;    // [Tp][O][8] records of the collision-probability cost (pred_mode 1): px, py, devx, devy, sx, sy, rho
+    int pred_mode;          // 0: inverse Mahalanobis (python path), 1: collision probability (cpp flavour)
     const float4* ohull32;  // [Tp][O]    fp32 copies (cx - origin, cy - origin, inflated radius, 0) for the warp-level cull
     const int* on_pred;     // [Tp] records per step
     const int* on_hull;     // [Tp]

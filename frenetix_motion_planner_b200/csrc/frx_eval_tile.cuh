@@ -599,15 +599,17 @@ __device__ __forceinline__ FrxLaneOut frx_candidate(const FrxKernelArgs& A, cons
             // x, y, theta of the candidate come back from the state tensor (L2), loaded ONE STEP AHEAD of their use
             const double* q = sp + (size_t)i0 * sstride;
             double x_n = 0.0, y_n = 0.0, th_n = 0.0;
-            if (i0 < i1) { x_n = __ldcg(q); y_n = __ldcg(q + fstride); if (need_col) th_n = __ldcg(q + 2 * fstride); }
+            const bool need_th = need_col;
+            if (i0 < i1) { x_n = __ldcg(q); y_n = __ldcg(q + fstride); if (need_th) th_n = __ldcg(q + 2 * fstride); }
             for (int i = i0; i < i1; ++i, q += sstride) {
                 const double x = x_n, y = y_n, th = th_n;
                 if (i + 1 < i1) {
                     x_n = __ldcg(q + sstride); y_n = __ldcg(q + sstride + fstride);
-                    if (need_col) th_n = __ldcg(q + sstride + 2 * fstride);
+                    if (need_th) th_n = __ldcg(q + sstride + 2 * fstride);
                 }
                 if (need_pred && i >= 1) {
                     // the obstacles predicted at this step: 48-byte records, warp-uniform 16-byte loads (frx_pred_step)
+                    // (the collision-probability flavour of this term always runs in frx_obstacle_kernel<1>)
                     const double xs[1] = {x}, ys[1] = {y};
                     const bool nd[1] = {true};
                     double acc[1] = {pred_sum};

@@ -172,6 +172,9 @@ __device__ __forceinline__ void frx_obs_block_finish(const FrxKernelArgs& A, Frx
     }
 }
 
+// PMODE: 0 = inverse-Mahalanobis prediction cost (python path), 1 = collision probability (cpp flavour) -- separate
+// instances so that the default one keeps its register budget
+template <int PMODE>
 __global__ void __launch_bounds__(FRX_OBS_THREADS, FRX_OBS_MIN_CTAS)
 frx_obstacle_kernel(const __grid_constant__ FrxKernelArgs A) {
     const int lane = threadIdx.x & 31;
@@ -222,13 +225,15 @@ frx_obstacle_kernel(const __grid_constant__ FrxKernelArgs A) {
         int col_k[R], bnd_k[R];          // ego hull index of the first hit (planner.py:370-372 reads the velocity there)
 #pragma unroll
         for (int u = 0; u < R; ++u) { pred_sum[u] = 0.0; d2o_sum[u] = 0.0; collide[u] = false; boundary[u] = false; col_k[u] = bnd_k[u] = 0; }
-        const bool w_pred = __any_sync(FULL, any_pred), w_col = __any_sync(FULL, any_col), w_d2o = __any_sync(FULL, any_d2o);
+        const bool w_pred = __any_sync(FULL, any_pred), w_d2o = __any_sync(FULL, any_d2o);
+        const bool w_sweep = __any_sync(FULL, any_col);            // some lane runs the collision sweep
+        const bool w_col = w_sweep || (w_pred && PMODE == 1);         // theta is needed (sweep, or the probability cost)
         if ((w_pred || w_d2o || w_col) && i0 < i1) {
             double pbx[R], pby[R], pux[R], puy[R];   // ego box of the previous step
             const double* q[R];
             double x1[R], y1[R], t1[R], x2[R], y2[R], t2[R];     // steps i + 1 and i + 2, in flight
             // a later chunk starts one step early: that step only yields the ego box the first hull needs
-            const int ifirst = (i0 > 0 && w_col) ? (i0 - 1) : i0;
+            const int ifirst = (i0 > 0 && w_sweep) ? (i0 - 1) : i0;
 #pragma unroll
             for (int u = 0; u < R; ++u) {
                 pbx[u] = pby[u] = pux[u] = puy[u] = 0.0;
@@ -253,8 +258,13 @@ frx_obstacle_kernel(const __grid_constant__ FrxKernelArgs A) {
                     q[u] += Np;
                 }
                 const bool warm = i < i0;                   // box-only step in front of a later chunk
-                if (w_pred && i >= 1 && !warm)
-                    frx_pred_step<R>(A.opred + (size_t)(i - 1) * A.O * FRX_PRED_REC, s_npred[i - 1], x, y, need_pred, pred_sum);
+                if (w_pred && i >= 1 && !warm) {
+                    if (PMODE == 0)
+                        frx_pred_step<R>(A.opred + (size_t)(i - 1) * A.O * FRX_PRED_REC, s_npred[i - 1], x, y, need_pred, pred_sum);
+                    else
+                        frx_prob_step<R>(A.oprob + (size_t)(i - 1) * A.O * FRX_PROB_REC, s_npred[i - 1], x, y, th, need_pred, pred_sum,
+                                         2 * A.half_len, 2 * A.half_wid);
+                }
                 if (w_d2o && !warm) {
 #pragma unroll
                     for (int u = 0; u < R; ++u) {
@@ -267,7 +277,7 @@ frx_obstacle_kernel(const __grid_constant__ FrxKernelArgs A) {
                         }
                     }
                 }
-                if (!w_col) continue;
+                if (!w_sweep) continue;
 #pragma unroll
                 for (int u = 0; u < R; ++u) {
                     // lanes that still have something to find; the set only shrinks, so a warp without one is done with
@@ -421,8 +431,9 @@ size_t frx_obstacle_scratch_elems(long long N) { return (size_t)8 * (size_t)N; }
 cudaError_t frx_launch_obstacle_pass(FrxKernelArgs& a, int sm_count, cudaStream_t st, int* launches) {
     static thread_local int occ = 0;
     if (occ == 0) {
-        cudaFuncSetAttribute(frx_obstacle_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 4);   // 8 KB shared, the rest L1
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, frx_obstacle_kernel, FRX_OBS_THREADS, 0) != cudaSuccess || occ < 1) occ = 1;
+        cudaFuncSetAttribute(frx_obstacle_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, 4);   // 8 KB shared, the rest L1
+        cudaFuncSetAttribute(frx_obstacle_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, 4);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, frx_obstacle_kernel<0>, FRX_OBS_THREADS, 0) != cudaSuccess || occ < 1) occ = 1;
         if (getenv("FRX_DEBUG")) fprintf(stderr, "[frx] obstacle kernel: %d blocks of %d threads per SM\n", occ, FRX_OBS_THREADS);
     }
     const long long full = (long long)sm_count * occ;
@@ -430,7 +441,8 @@ cudaError_t frx_launch_obstacle_pass(FrxKernelArgs& a, int sm_count, cudaStream_
     const long long row_blocks = (a.N + FRX_OBS_THREADS * FRX_OBS_ROWS - 1) / (FRX_OBS_THREADS * FRX_OBS_ROWS);
     const long long want = row_blocks * a.obs_chunks;
     const int grid = (int)(want < full ? want : full);
-    frx_obstacle_kernel<<<grid, FRX_OBS_THREADS, 0, st>>>(a);
+    if (a.pred_mode == 1) frx_obstacle_kernel<1><<<grid, FRX_OBS_THREADS, 0, st>>>(a);
+    else frx_obstacle_kernel<0><<<grid, FRX_OBS_THREADS, 0, st>>>(a);
     *launches = 1;
     if (a.obs_chunks > 1) {
         long long fg = (a.N + FRX_OBS_THREADS - 1) / FRX_OBS_THREADS;

@@ -113,8 +113,9 @@ class ReactivePlannerB200:
         self._kinematic_debug = bool(_get(debug, "kinematic_debug", True))
         # "cpp" sampling adds {N*dT}, {ss0} to the level sets like reactive_planner_cpp.py:235-237
         self.sampling_style = _get(debug, "sampling_style", "python")
-        # the other two things ReactivePlannerCpp does differently on the hot path (reactive_planner_cpp.py:109-112,
-        # 170-178): curvature-rate limit from vehicle.v_delta_max, velocity-offset cost with norm_order = 2
+        # the other things ReactivePlannerCpp does differently on the hot path (reactive_planner_cpp.py:109-112, 151-155,
+        # 170-178): curvature-rate limit from vehicle.v_delta_max, prediction cost = collision probability
+        # (CalculateCollisionProbabilityFast), velocity-offset cost with norm_order = 2
         self.cpp_flavour = bool(_get(debug, "cpp_flavour", False))
         if self.cpp_flavour:
             self.sampling_style = "cpp"
@@ -339,7 +340,7 @@ class ReactivePlannerB200:
                      cost_names=self.cost_names, cost_weights=self.cost_weight_list, store_states=True,
                      check_collisions=self.collision_check_enabled and (self.use_prediction or self.static_obbs is not None),
                      curvature_rate_from_v_delta=self.cpp_flavour, v_delta_max=_get(vp, "v_delta_max", 0.4),
-                     velocity_offset_norm=2 if self.cpp_flavour else 1)
+                     velocity_offset_norm=2 if self.cpp_flavour else 1, prediction_cost_mode=1 if self.cpp_flavour else 0)
         if self._ref_dirty:
             if getattr(self, "_device_tables", None) is not cs:       # device-built tables are already where they belong
                 ref = np.asarray(cs.reference)

@@ -119,6 +119,11 @@ typedef struct frx_params {
     int32_t velocity_offset_norm;        /* 2: CalculateVelocityOffsetCost(..., norm_order=2) (reactive_planner_cpp.py:170-178):
                                             squared instead of absolute offsets over the second half of the horizon */
     double v_delta_max;                  /* vehicle.v_delta_max (steering rate limit), used when curvature_rate_from_v_delta */
+    int32_t prediction_cost_mode;        /* 1: the prediction term is CalculateCollisionProbabilityFast (reactive_planner_cpp.py:
+                                            151-155), i.e. get_collision_probability_fast (risk_assessment/
+                                            collision_probability.py:141-261) summed over steps and obstacles; 0: inverse
+                                            Mahalanobis distance (python path) */
+    int32_t reserved_;
 } frx_params;
 
 typedef struct frx_result {

@@ -93,6 +93,8 @@ def plan(sampling, ref: fo.RefPath, prm: fo.Params, predictions=(), static_obbs=
          T_values=None, buffers=None, library=None):
     """`buffers`: dict reused across calls (timing runs: keeps page faults of fresh arrays out of the loop).
     `nthreads` > 0 overrides OMP_NUM_THREADS (torchrun exports 1).  `library`: native_lib() for timing runs."""
+    if getattr(prm, "prediction_cost_mode", 0) != 0:
+        raise NotImplementedError("the C oracle only has the inverse-Mahalanobis prediction cost (use frenet_oracle.plan)")
     L = library or lib()
     S = np.ascontiguousarray(sampling, dtype=np.float64)
     n = S.shape[0]

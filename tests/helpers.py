@@ -64,7 +64,8 @@ def configure_handler(h, ref, prm, preds, static_obbs=None, sampling=None, T_val
                  desired_velocity=prm.desired_velocity, cost_names=names,
                  cost_weights=[prm.cost_weights[n] for n in names], store_states=store_states,
                  check_collisions=check_collisions, curvature_rate_from_v_delta=prm.curvature_rate_from_v_delta,
-                 v_delta_max=prm.v_delta_max, velocity_offset_norm=prm.velocity_offset_norm)
+                 v_delta_max=prm.v_delta_max, velocity_offset_norm=prm.velocity_offset_norm,
+                 prediction_cost_mode=prm.prediction_cost_mode)
     h.set_reference(ref.ref_pos, ref.ref_theta, ref.ref_curv, ref.ref_curv_d, ref.ref_x, ref.ref_y)
     if T_values is None:
         T_values = hotpath.distinct_durations(sampling)

@@ -21,14 +21,14 @@ class OracleHandler:
     def set_params(self, *, dt, N, low_vel_mode, draw_traj_set, kinematic_debug, a_max, v_switch, delta_max, wheelbase,
                    wb_rear_axle, length, width, x0_orientation, desired_velocity, cost_names, cost_weights,
                    store_states=True, check_collisions=True, curvature_rate_from_v_delta=False, v_delta_max=0.4,
-                   velocity_offset_norm=1):
+                   velocity_offset_norm=1, prediction_cost_mode=0):
         self._prm = fo.Params(dt=dt, N=N, a_max=a_max, v_switch=v_switch, delta_max=delta_max, wheelbase=wheelbase,
                               wb_rear_axle=wb_rear_axle, length=length, width=width, low_vel_mode=bool(low_vel_mode),
                               x0_orientation=x0_orientation, desired_velocity=desired_velocity,
                               draw_traj_set=bool(draw_traj_set), kinematic_debug=bool(kinematic_debug),
                               cost_weights=dict(zip(cost_names, cost_weights)),
                               curvature_rate_from_v_delta=bool(curvature_rate_from_v_delta), v_delta_max=v_delta_max,
-                              velocity_offset_norm=int(velocity_offset_norm))
+                              velocity_offset_norm=int(velocity_offset_norm), prediction_cost_mode=int(prediction_cost_mode))
         self._check = bool(check_collisions)
         self.n_costs, self.Nt = len(cost_names), N + 1
 
@@ -61,8 +61,9 @@ class OracleHandler:
     # ---- plans
     def _run(self, S, row_base):
         self.generation += 1
-        out = c_oracle.plan(S, self._ref, self._prm, self._preds if self._check else [], static_obbs=self._static if self._check else None,
-                            check_all_collisions=True, collision_check=self._check)
+        plan = fo.plan if self._prm.prediction_cost_mode == 1 else c_oracle.plan      # the C port has no collision-probability cost
+        out = plan(S, self._ref, self._prm, self._preds if self._check else [], static_obbs=self._static if self._check else None,
+                   check_all_collisions=True, collision_check=self._check)
         self._out, self._row_base, self.n_rows = out, row_base, S.shape[0]
         res = _capi.FrxResult()
         res.argmin = out["argmin"] + row_base if out["argmin"] >= 0 else -1

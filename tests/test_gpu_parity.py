@@ -225,3 +225,40 @@ def test_static_boxes_fused_pass_tile_cull_equals_oracle(name, seg, monkeypatch)
         dev = device_plan(S, ref, prm, preds, static_obbs=boxes)
         compare_with_oracle(dev, ora, prm)
     assert (fo.plan(S, ref, prm, preds, static_obbs=walls)["flags"] & fo.FLAG_BOUNDARY).any()
+
+
+@pytest.mark.parametrize("correlated", [False, True])
+@pytest.mark.parametrize("name", ["arc_hv_draw_pred", "tjunction_draw", "scurve_lowvel_nodraw"])
+def test_collision_probability_prediction_cost_matches_the_oracle(name, correlated, monkeypatch):
+    """prediction term = CalculateCollisionProbabilityFast (reactive_planner_cpp.py:151-155 = the in-tree
+    get_collision_probability_fast): bivariate-normal rectangle probabilities on the device (Genz's BVND, all three |rho|
+    branches) against the oracle restatement that is pinned to the reference's own function; small plans (forced into the
+    split obstacle kernel) and step-chunked ones."""
+    import dataclasses
+    g, ref, prm, preds = load_golden(name)
+    preds = [dict(p) for p in preds]
+    S = g["sampling"]
+    if correlated:
+        ego = np.array([ref.ref_x[int(np.argmax(ref.ref_pos > S[0, 2]))], ref.ref_y[int(np.argmax(ref.ref_pos > S[0, 2]))]])
+        for o, p in enumerate(preds):
+            cov = np.array(p["cov_list"], dtype=float).copy()
+            for k in range(cov.shape[0]):
+                r = [0.5, -0.8, 0.95, -0.97, 0.2, 0.0][(k + o) % 6]
+                sx, sy = 0.4 + 0.03 * k, 0.6 + 0.02 * k
+                cov[k] = [[sx * sx, r * sx * sy], [r * sx * sy, sy * sy]]
+            cov[2] = 0.0                                                      # ground-truth style zero covariance
+            p["cov_list"] = cov
+            p["pos_list"] = np.array(p["pos_list"]) + (ego - np.array(p["pos_list"])[3]) * 0.8     # pull them next to the ego
+    p1 = dataclasses.replace(prm, prediction_cost_mode=1)
+    ora = fo.plan(S, ref, p1, preds)
+    k = list(ora["cost_names"]).index("prediction")
+    costed = (ora["flags"] & fo.FLAG_COSTED) != 0
+    assert (ora["costs"][costed, k] > 0).sum() > 10                           # the term is alive in this case
+    for chunks in ("1", "4"):
+        monkeypatch.setenv("FRX_OBS_CHUNKS", chunks)
+        dev = device_plan(S, ref, p1, preds)
+        assert dev["res"].obstacle_kernel_ms > 0
+        alts = band_alternatives(S, ref, p1, preds, np.flatnonzero(ora["margins"] < BAND))
+        compare_with_oracle(dev, ora, p1, alts=alts)
+    base = fo.plan(S, ref, prm, preds)
+    assert not np.allclose(base["costs"][costed, k], ora["costs"][costed, k])
