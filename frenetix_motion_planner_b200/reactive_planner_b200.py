@@ -117,6 +117,7 @@ class ReactivePlannerB200:
         # 170-178): curvature-rate limit from vehicle.v_delta_max, prediction cost = collision probability
         # (CalculateCollisionProbabilityFast), velocity-offset cost with norm_order = 2
         self.cpp_flavour = bool(_get(debug, "cpp_flavour", False))
+        self.emergency_mode = _get(planning, "emergency_mode", "risk")      # planning.yaml: "stopping" | "risk" (cpp path)
         if self.cpp_flavour:
             self.sampling_style = "cpp"
         # True: the reference tables and the Frenet initial state are computed on the device (frx_set_reference_polyline,
@@ -463,8 +464,37 @@ class ReactivePlannerB200:
         if res.argmin >= 0:
             return bundle.sample(res.argmin - bundle.row_base).detach()
         if samp_lvl >= self._sampling_max - 1 and res.n_feasible > 0:
+            if self.cpp_flavour and self.emergency_mode == "stopping":
+                # reactive_planner_cpp.py:403-407: lowest end velocity, then shortest duration, then the lateral target
+                # closest to the current offset, among the feasible candidates
+                fl = bundle.flags
+                feas = np.flatnonzero(((fl & _capi.FLAG_VALID) != 0) & ((fl & _capi.FLAG_FEASIBLE) != 0) &
+                                      ((fl & _capi.FLAG_IN_LIST) != 0))
+                self.msg_logger.warning("No optimal trajectory available. Select stopping trajectory!")
+                params = np.array([bundle.sampling_row(int(r)) for r in feas]) if feas.size < 4096 else bundle.sampling_rows(feas)
+                pick = self._select_stopping_row(params, self.x_cl[1][0])
+                return bundle.sample(int(feas[pick])).detach()
             return self._select_min_risk(bundle)
         return None
+
+    @staticmethod
+    def _select_stopping_row(params: np.ndarray, d_pos: float) -> int:
+        """Index into `params` ([n, 13] sampling rows of the feasible candidates) of the trajectory
+        ReactivePlannerCpp._select_stopping_trajectory (reactive_planner_cpp.py:446-469) returns: the first hit when
+        iterating end velocities ascending, durations ascending, lateral targets by distance to `d_pos`."""
+        v, t, d = params[:, 5], params[:, 1], params[:, 10]
+        d_vals = np.unique(d)
+        d_rank = {val: k for k, val in enumerate(d_vals[np.argsort(np.abs(d_vals - d_pos))])}
+        rank = np.array([d_rank[val] for val in d])
+        return int(np.lexsort((rank, t, v))[0])
+
+    @staticmethod
+    def _select_stopping_trajectory(trajectories, sampling_matrix, d_pos):
+        """Same call as the reference's static method: picks from a list of samples."""
+        if not trajectories:
+            return None
+        params = np.array([t.sampling_parameters for t in trajectories])
+        return trajectories[ReactivePlannerB200._select_stopping_row(params, d_pos)]
 
     def _select_min_risk(self, bundle: TrajectoryBundle):
         """reactive_planner.py:262-269: no collision-free candidate at the last level -> the feasible trajectory with the

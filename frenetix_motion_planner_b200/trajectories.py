@@ -22,6 +22,7 @@ import numpy as np
 from . import _capi
 
 _UNSET = object()
+_PREFETCH = 256          # rows gathered at once when a list of samples is being iterated
 # risk_assessment harm model LR1S "ignore_angle" (configurations/harm_parameters.json: log_reg.ignore_angle)
 DEFAULT_HARM_COEFF = {"const": -4.591, "speed": 0.185}
 _CART = ("x", "y", "theta", "v", "a", "kappa", "kappa_dot")
@@ -261,8 +262,16 @@ class _SampleList:
         return self._b.sample(int(self._rows[i]))
 
     def __iter__(self):
-        for r in self._rows:
-            yield self._b.sample(int(r))
+        # sinks that walk the whole list and read the state arrays of every sample (logging_helpers.py:275-294,580-647,
+        # visualisation) would otherwise issue one device gather per sample: while iterating, a state miss fetches the
+        # block of rows around it in one gather
+        rows = self._rows
+        for k0 in range(0, rows.size, _PREFETCH):
+            block = rows[k0:k0 + _PREFETCH]
+            for r in block:
+                self._b._prefetch_hint = block
+                yield self._b.sample(int(r))
+        self._b._prefetch_hint = None
 
     def __bool__(self):
         return self._rows.size > 0
@@ -290,6 +299,8 @@ class TrajectoryBundle:
         self._is_sorted = False
         self.winner_row: Optional[int] = None     # local row of the last plan's arg-min (set by the planner)
         self._gen = getattr(handler, "generation", 0)     # the plan these views belong to
+        self._prefetch_hint = None                        # rows of the block a list iteration is currently in
+        self._state_cache: Dict[int, np.ndarray] = {}
         self.harm_coeff = dict(DEFAULT_HARM_COEFF)
 
     def _live(self):
@@ -329,10 +340,21 @@ class TrajectoryBundle:
         return self._total
 
     def states_of(self, row: int) -> np.ndarray:
+        hit = self._state_cache.pop(int(row), None)
+        if hit is not None:
+            return hit
         self._live()
         if self.winner_row is not None and int(row) == self.winner_row:
             # the selected candidate's rows came back with the arg-min (mapped result record): no device round trip
             return self._h.winner_states()
+        hint = self._prefetch_hint
+        if hint is not None and hint.size > 1 and int(row) in hint:
+            st = self._h.get_states(np.asarray(hint, dtype=np.int64))
+            for k, r in enumerate(hint.tolist()):
+                if r != int(row):
+                    self._state_cache[r] = st[:, k, :]
+            self._prefetch_hint = None            # one gather per block
+            return st[:, hint.tolist().index(int(row)), :]
         return self._h.get_states(np.array([row], dtype=np.int64))[:, 0, :]
 
     def states(self, rows, fields=None) -> np.ndarray:
@@ -349,6 +371,21 @@ class TrajectoryBundle:
         iv, idd = divmod(rem, len(d1))
         (s0, ss0, sss0), (d0, dd0, ddd0) = x_cl
         return np.array([0.0, t1[it], s0, ss0, sss0, v1[iv], 0.0, d0, dd0, ddd0, d1[idd], 0.0, 0.0])
+
+    def sampling_rows(self, rows) -> np.ndarray:
+        """[len(rows), 13] sampling rows, vectorised (grid mode computes them from the axes)."""
+        rows = np.asarray(rows, dtype=np.int64)
+        if self._sampling is not None:
+            return np.array(self._sampling[rows], dtype=np.float64)
+        t1, v1, d1, x_cl = self._grid
+        g = self._row_first + rows
+        it, rem = np.divmod(g, len(v1) * len(d1))
+        iv, idd = np.divmod(rem, len(d1))
+        (s0, ss0, sss0), (d0, dd0, ddd0) = x_cl
+        out = np.zeros((rows.size, 13))
+        out[:, 1], out[:, 5], out[:, 10] = np.asarray(t1)[it], np.asarray(v1)[iv], np.asarray(d1)[idd]
+        out[:, 2], out[:, 3], out[:, 4], out[:, 7], out[:, 8], out[:, 9] = s0, ss0, sss0, d0, dd0, ddd0
+        return out
 
     # ---- list semantics of the reference ---------------------------------------------------
     def sample(self, row: int) -> TrajectorySample:

@@ -14,6 +14,7 @@ GPU part (no reference tree on the GPU box): the planner calls recorded in the t
 must give the same selected trajectories, costs and counters; the batched launch is checked against the ORACLE per agent.
 """
 import inspect
+import json
 import os
 import re
 import sys
@@ -81,6 +82,28 @@ def test_public_surface_of_the_reference_planner_classes_is_present():
     assert not absent, f"instance attributes missing: {sorted(absent)}"
 
 
+@needs_reference
+def test_stopping_trajectory_selection_equals_the_reference_static_method():
+    """reactive_planner_cpp.py:446-469 (emergency_mode == "stopping"), on random feasible subsets of a cpp-style grid."""
+    import ref_stubs
+    ref_stubs.install()
+    from frenetix_motion_planner.reactive_planner_cpp import ReactivePlannerCpp
+    from frenetix_motion_planner_b200 import ReactivePlannerB200
+    rng = np.random.default_rng(4)
+    t1, v1, d1 = np.round(np.arange(11, 31, 3) * 0.1, 2), np.linspace(0.001, 9.0, 10), np.append(np.linspace(-3, 3, 9), 0.37)
+    S = syn.grid_sampling_matrix(t1, v1, d1, ([5.0, 4.0, 0.0], [0.37, 0.0, 0.0]))
+    for _ in range(200):
+        keep = np.flatnonzero(rng.random(S.shape[0]) < rng.uniform(0.01, 0.5))
+        if keep.size == 0:
+            continue
+        rng.shuffle(keep)
+        trajs = [types.SimpleNamespace(sampling_parameters=S[r], row=int(r)) for r in keep]
+        d_pos = float(rng.uniform(-3, 3))
+        want = ReactivePlannerCpp._select_stopping_trajectory(trajs, S, d_pos)
+        got = ReactivePlannerB200._select_stopping_trajectory(trajs, S, d_pos)
+        assert got.row == want.row
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # (ii) FrenetPlannerInterface drives the planner
 # ---------------------------------------------------------------------------------------------------------------
@@ -105,6 +128,53 @@ def test_reference_interface_drives_the_planner_for_three_replanning_cycles():
     assert first.initial_state.time_step == 0
     kept = out["s0_opt_states"]
     assert np.array_equal(kept, g["s0_opt_states"])
+
+
+@needs_reference
+def test_reference_sql_logger_writes_the_full_trajectory_set(tmp_path):
+    """SURVEY 8f-4, logging sinks: the reference's own SqlLogger.log_all_trajectories (logging_helpers.py:275-294) walks
+    planner.all_traj and reads every attribute of the sample surface (cartesian / curvilinear arrays, costMap,
+    feasabilityMap, sampling_parameters, _ego_risk, _coll_detected, boundary_harm ...).  It runs unmodified on the B200
+    planner's lazy samples, with one device gather per 256 trajectories instead of one per trajectory."""
+    from pathlib import Path
+    _, _, FrenetPlannerInterface = _reference_classes()
+    from frenetix_motion_planner.utility.logging_helpers import SqlLogger
+    from oracle_handler import OracleHandler
+    import make_interface_trace as mit
+    from frenetix_motion_planner_b200 import ReactivePlannerB200
+    fx, lanelets = mit.fixture()
+    cfg_plan, cfg_sim = mit.configs()
+
+    class Counting(OracleHandler):
+        gathers = 0
+
+        def get_states(self, idx, fields=None):
+            Counting.gathers += 1
+            return super().get_states(idx, fields)
+    planner = ReactivePlannerB200(cfg_plan, cfg_sim, None, None, None, None, None, handler=Counting())
+    it = mit.make_interface(FrenetPlannerInterface, planner, fx, lanelets, cfg_plan, cfg_sim)
+    it.update_planner(types.SimpleNamespace(lanelet_network=None), mit.predictions_at(fx, 0))
+    it.step_interface(0)
+    sql = SqlLogger(Path(tmp_path), cfg_plan, cfg_sim, None, None)
+    sql.set_cost_names(list(planner.cost_names))
+    n = len(planner.all_traj)
+    before = Counting.gathers
+    sql.log_all_trajectories(planner.all_traj, 0)
+    assert Counting.gathers - before <= -(-n // 256) + 1
+    con = sql.con                                   # (the logger holds the database in EXCLUSIVE locking mode)
+    assert con.execute("SELECT COUNT(*) FROM trajectories").fetchone()[0] == n == 630
+    b = planner._bundle
+    row = planner.all_traj[7].uniqueId
+    x_txt, = con.execute("SELECT x FROM trajectories WHERE id = ?", (str(row),)).fetchone()
+    assert np.allclose(np.array(json.loads(x_txt)), b._h.get_states(np.array([row]))[0, 0], rtol=1e-4)
+    cost, = con.execute("SELECT costs_cumulative_weighted FROM costs WHERE id = ?", (row,)).fetchone()
+    assert cost == b.total[row]
+    feas = con.execute("SELECT feasible, inf_curvature FROM infeasability WHERE id = ?", (row,)).fetchone()
+    assert bool(feas[0]) == bool(b.flags[row] & 2)
+    t1, d1 = con.execute("SELECT t1, d1 FROM sampling_params WHERE id = ?", (row,)).fetchone()
+    assert (t1, d1) == (b.sampling_row(row)[1], b.sampling_row(row)[10])
+    harm = [r[0] for r in con.execute("SELECT boundary_harm FROM trajectories_meta")]
+    assert sum(h > 0 for h in harm) == int(((b.flags & (1 << 13)) != 0).sum()) > 0
 
 
 @needs_reference
