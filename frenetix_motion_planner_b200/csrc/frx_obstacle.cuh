@@ -260,7 +260,8 @@ frx_obstacle_kernel(const __grid_constant__ FrxKernelArgs A) {
                 const bool warm = i < i0;                   // box-only step in front of a later chunk
                 if (w_pred && i >= 1 && !warm) {
                     if (PMODE == 0)
-                        frx_pred_step<R>(A.opred + (size_t)(i - 1) * A.O * FRX_PRED_REC, s_npred[i - 1], x, y, need_pred, pred_sum);
+                        frx_pred_step<R>(A.opred + (size_t)(i - 1) * A.O * FRX_PRED_REC, s_npred[i - 1], x, y, need_pred, pred_sum, ox, oy,
+                                         A.obs, A.Tp, i - 1);
                     else
                         frx_prob_step<R>(A.oprob + (size_t)(i - 1) * A.O * FRX_PROB_REC, s_npred[i - 1], x, y, th, need_pred, pred_sum,
                                          2 * A.half_len, 2 * A.half_wid);

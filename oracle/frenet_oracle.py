@@ -824,7 +824,9 @@ def plan(sampling: np.ndarray, ref: RefPath, prm: Params, predictions: Sequence[
     names = prm.active_costs()
     K = len(names)
     weights = [prm.cost_weights[k] for k in names]
-    inv_covs = [np.linalg.inv(np.asarray(p["cov_list"], dtype=float)) for p in predictions]
+    # (the collision-probability flavour never inverts a covariance: zero matrices mark ground-truth predictions there)
+    inv_covs = [np.linalg.inv(np.asarray(p["cov_list"], dtype=float)) for p in predictions] \
+        if prm.prediction_cost_mode == 0 else [None] * len(predictions)
 
     states = np.zeros((14, n, Nt))
     flags = np.zeros(n, dtype=np.uint32)

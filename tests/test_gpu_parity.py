@@ -262,3 +262,31 @@ def test_collision_probability_prediction_cost_matches_the_oracle(name, correlat
         compare_with_oracle(dev, ora, p1, alts=alts)
     base = fo.plan(S, ref, prm, preds)
     assert not np.allclose(base["costs"][costed, k], ora["costs"][costed, k])
+
+
+def test_prediction_cost_exact_fallback(monkeypatch):
+    """The fast prediction-cost path factors the inverse covariance (Cholesky) and shares reciprocals; covariances without a
+    factor (indefinite) and an ego that sits exactly ON a predicted mean (the reference returns inf) must take the exact
+    term-by-term fallback -- fused pass, split pass and chunked pass."""
+    g, ref, prm, preds = load_golden("arc_hv_draw_pred")
+    S = g["sampling"]
+    ora0 = fo.plan(S, ref, prm, preds)
+    preds = [dict(p) for p in preds]
+    cov = np.array(preds[0]["cov_list"], dtype=float).copy()
+    cov[4] = [[1.0, 2.0], [2.0, 1.0]]                      # indefinite
+    cov[9] = [[0.3, 0.1], [0.25, 0.4]]                     # not symmetric (the quadratic form only sees the symmetric part)
+    preds[0]["cov_list"] = cov
+    pos = np.array(preds[1]["pos_list"], dtype=float).copy()
+    r = int(np.flatnonzero((ora0["flags"] & fo.FLAG_COSTED) != 0)[17])
+    pos[6] = [ora0["states"][fo.F_X][r, 7], ora0["states"][fo.F_Y][r, 7]]       # obstacle mean == ego position of row r at step 7
+    preds[1]["pos_list"] = pos
+    ora = fo.plan(S, ref, prm, preds)
+    k = list(ora["cost_names"]).index("prediction")
+    assert np.isinf(ora["costs"][r, k])
+    for split, chunks in (("0", "1"), ("1", "1"), ("1", "4")):
+        monkeypatch.setenv("FRX_SPLIT_OBS", split)
+        monkeypatch.setenv("FRX_OBS_CHUNKS", chunks)
+        dev = device_plan(S, ref, prm, preds)
+        assert np.isinf(dev["costs"][r, k]) and np.isinf(dev["total"][r])
+        alts = band_alternatives(S, ref, prm, preds, np.flatnonzero(ora["margins"] < BAND))
+        compare_with_oracle(dev, ora, prm, alts=alts)
