@@ -238,29 +238,44 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------
 # CPU arms
 # ----------------------------------------------------------------------------------------------
-def cpu_port():
-    """The C/OpenMP port of the reference's Python path, built for THIS host (-O3 -march=native, contraction off)."""
-    from oracle import c_oracle
-    return c_oracle, c_oracle.native_lib()
+def cpu_abi_handler(w, S):
+    """The reference's CPU path behind the SAME C ABI the GPU arm is called through: oracle/cpu_abi (include/frx.h on the
+    host cores = the C/OpenMP port of the reference's Python path with its lazy collision walk), built for THIS host
+    (-O3 -march=native, contraction off) and configured exactly like the device handler."""
+    from oracle.build import build_cpu_abi
+    from frenetix_motion_planner_b200 import _capi, hotpath
+    threads = host_threads()
+    os.environ["FRX_CPU_THREADS"] = str(threads)               # torchrun exports OMP_NUM_THREADS=1; the CPU arm ignores that
+    lib = _capi.load_library(path=build_cpu_abi(native=True))
+    lib.orc_last_threads.restype = __import__("ctypes").c_int
+    h = _capi.Handler(0, library=lib)
+    cs = CoordinateSystem(w["polyline"])
+    names, weights = hotpath.active_costs(syn.DEFAULT_COST_WEIGHTS)
+    veh = syn.VEHICLE_2
+    h.set_params(dt=w["dt"], N=w["N"], low_vel_mode=w["v0"] < 2.0, draw_traj_set=True, kinematic_debug=True,
+                 a_max=veh["a_max"], v_switch=veh["v_switch"], delta_max=veh["delta_max"], wheelbase=veh["wheelbase"],
+                 wb_rear_axle=veh["wb_rear_axle"], length=veh["length"], width=veh["width"],
+                 x0_orientation=w["x0_orientation"], desired_velocity=w["v_des"], cost_names=names,
+                 cost_weights=weights, store_states=True, check_collisions=True)
+    h.set_reference(cs.ref_pos, cs.ref_theta, cs.ref_curv, cs.ref_curv_d, w["polyline"][:, 0], w["polyline"][:, 1])
+    h.set_time_tables(*hotpath.time_tables(np.unique(S[:, 1]), w["dt"], w["N"] + 1))
+    packed = hotpath.pack_predictions(w["preds"])
+    if packed is not None:
+        h.set_predictions(*packed)
+    return h, lib, threads
 
 
 def cpu_port_throughput(w, S, budget_s=12.0, min_reps=2, max_reps=200):
-    """Time the C/OpenMP port (lazy collision walk like planner.py:329-392) on `S` with all host threads;
-    returns (cand/s, threads, reps, seconds).  Output arrays are allocated once and reused."""
-    c_oracle, lib = cpu_port()
-    ref, prm = oracle_inputs(w)
-    threads = host_threads()
-    Tv = np.unique(S[:, 1])
-    buf = {}
-    kw = dict(check_all_collisions=False, want_states=True, want_margins=False, T_values=Tv, buffers=buf, nthreads=threads,
-              library=lib)
-    c_oracle.plan(S, ref, prm, w["preds"], **kw)              # warm-up (threads, pages)
+    """Time the CPU implementation of the ABI on `S` with all host threads; returns (cand/s, threads, reps, seconds)."""
+    h, lib, threads = cpu_abi_handler(w, S)
+    h.plan(S)                                                  # warm-up (threads, pages)
     reps, t_acc = 0, 0.0
     while reps < min_reps or (t_acc < budget_s and reps < max_reps):
         t0 = time.perf_counter()
-        c_oracle.plan(S, ref, prm, w["preds"], **kw)
+        h.plan(S)
         t_acc += time.perf_counter() - t0
         reps += 1
+    assert int(lib.orc_last_threads()) == threads, "CPU arm did not get every host thread"
     return S.shape[0] * reps / t_acc, threads, reps, t_acc
 
 
@@ -299,33 +314,30 @@ def oracle_confirms_winner(w, n_total: int, winner_row: int, winner_cost: float,
 
 
 def run_reference_arm(args, w, world):
-    """--impl reference: the reference's CPU path on the host cores.  The reference itself (pure
-    Python + un-vendored frenetix/commonroad wheels) cannot be installed offline, so this times the
-    C/OpenMP port in oracle/ (DESIGN.md section 6), with every hardware thread of the host."""
-    c_oracle, lib = cpu_port()
+    """--impl reference: the reference's CPU path on the host cores.  The reference itself (pure Python + un-vendored
+    frenetix/commonroad wheels) cannot be installed offline, so this times the C/OpenMP port of its Python path behind
+    the same C ABI (oracle/cpu_abi), with every hardware thread of the host."""
     n_total = w["t1"].size * w["v1"].size * w["d1"].size
     rows = n_total if w["scaling"] == "strong" else n_total // world     # the workload of ONE GPU-arm rank 0 step
     target = 100_000 if w["preds"] else 200_000
     idx = cpu_sample_indices(w, n_total, 0, rows, target)
     S = grid_rows(w, idx)
-    ref, prm = oracle_inputs(w)
-    threads = host_threads()
-    Tv = np.unique(S[:, 1])
-    buf = {}
-    kw = dict(check_all_collisions=False, want_states=True, want_margins=False, T_values=Tv, buffers=buf, nthreads=threads,
-              library=lib)
+    h, lib, threads = cpu_abi_handler(w, S)
     vals = []
     for i in range(args.warmup + args.steps):
         t0 = time.perf_counter()
-        c_oracle.plan(S, ref, prm, w["preds"], **kw)
+        r = h.plan(S)
+        if r.argmin >= 0:
+            h.winner_states()
         if i >= args.warmup:
             vals.append(time.perf_counter() - t0)
-    assert threads == host_threads() and c_oracle.threads_used(lib) == threads, "CPU arm did not get every host thread"
+    assert int(lib.orc_last_threads()) == threads == host_threads(), "CPU arm did not get every host thread"
     sec_per_step = float(np.mean(vals))
     value = S.shape[0] / sec_per_step
-    sample = (f"each step = every {max(1, rows // target)}-th row of the workload ({S.shape[0]:,} of {rows:,} rows), "
-              f"C/OpenMP port of the reference Python path (oracle/c/frx_oracle.c, gcc -O3 -march=native "
-              f"-ffp-contract=off) on {threads} threads; frenetix 0.4.0 / the Python reference are not installable offline")
+    sample = (f"each step = every {max(1, rows // target)}-th row of the workload ({S.shape[0]:,} of {rows:,} rows) through "
+              f"frx_plan of the CPU implementation of the C ABI (oracle/cpu_abi: C/OpenMP port of the reference's Python path, "
+              f"gcc -O3 -march=native -ffp-contract=off) on {threads} threads; frenetix 0.4.0 / the Python reference are not "
+              f"installable offline")
     emit({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec_per_step * 1e3, "higher_is_better": True, "scaling": w["scaling"],
@@ -761,8 +773,8 @@ def run_gpu_workload(env: Env, name: str, steps: int, warmup: int, cpu_baseline:
             line["cpu_baseline"] = {
                 "value": thr, "unit": UNIT, "cores": threads, "kind": "port",
                 "sample": f"{reps} x every {max(1, count // S_cpu.shape[0])}-th row of the workload "
-                          f"({S_cpu.shape[0]:,} rows, {secs:.1f} s), C/OpenMP port of the reference's Python path "
-                          f"(oracle/c/frx_oracle.c, gcc -O3 -march=native -ffp-contract=off)",
+                          f"({S_cpu.shape[0]:,} rows, {secs:.1f} s) through the CPU implementation of the C ABI (oracle/cpu_abi: "
+                          f"C/OpenMP port of the reference's Python path, gcc -O3 -march=native -ffp-contract=off)",
                 "python_path_1core": python_path_throughput(w, S_cpu) if headline else None}
     if page is not None:
         page.close()

@@ -151,8 +151,10 @@ class Handler:
     """Thin object wrapper of one ``frx_ctx`` (the counterpart of ``frenetix.TrajectoryHandler``,
     reactive_planner_cpp.py:49): owns the device buffers of one planner instance."""
 
-    def __init__(self, device: int = 0):
-        self._lib = load_library()
+    def __init__(self, device: int = 0, library=None):
+        # `library`: another build of the same ABI loaded with load_library(path) (tuning builds; the benchmark's CPU arm
+        # binds the host-core implementation of the ABI this way).  The package itself always uses libfrx_b200.so.
+        self._lib = library if library is not None else load_library()
         self._ctx = C.c_void_p()
         rc = self._lib.frx_create(int(device), C.byref(self._ctx))
         if rc != 0 or not self._ctx:

@@ -37,6 +37,26 @@ def build(force=False):
     return _compile(OUT, ["-O2"], force)
 
 
+ABI_SRC = os.path.join(HERE, "cpu_abi", "frx_cpu.c")
+INCLUDE = os.path.join(os.path.dirname(HERE), "include")
+
+
+def build_cpu_abi(native=False, force=False):
+    """The C ABI of include/frx.h on the host cores (oracle/cpu_abi/frx_cpu.c + the port) -> libfrx_cpu_omp[_native_<cpu>].so.
+    Baseline / test infrastructure: bench.py's reference arm times the CPU path through the same calls as the GPU path."""
+    os.makedirs(OUT_DIR, exist_ok=True)
+    out = os.path.join(OUT_DIR, f"libfrx_cpu_omp_native_{_cpu_key()}.so" if native else "libfrx_cpu_omp.so")
+    newest = max(os.path.getmtime(SRC), os.path.getmtime(ABI_SRC), os.path.getmtime(os.path.join(INCLUDE, "frx.h")))
+    if not force and os.path.exists(out) and os.path.getmtime(out) >= newest:
+        return out
+    tmp = f"{out}.{os.getpid()}.tmp"
+    cmd = ["gcc"] + (["-O3", "-march=native"] if native else ["-O2"]) + COMMON + ["-I", INCLUDE, "-o", tmp, ABI_SRC, SRC, "-lm"]
+    print("[oracle build]", " ".join(cmd), file=sys.stderr, flush=True)
+    subprocess.check_call(cmd)
+    os.replace(tmp, out)
+    return out
+
+
 def _cpu_key() -> str:
     try:
         with open("/proc/cpuinfo") as f:
@@ -55,3 +75,4 @@ def build_native(force=False):
 
 if __name__ == "__main__":
     build(force="--force" in sys.argv)
+    build_cpu_abi(force="--force" in sys.argv)
