@@ -143,6 +143,7 @@ struct FrxKernelArgs {
     int defer_obs;          // 1: the eval kernel skips the obstacle pass, arg-min and result record; frx_obstacle_kernel
                             //    (launched right behind it) does them
     int keep_xyt;           // store_states == 0 but the obstacle pass needs the x, y, theta planes
+    int obs_stage_steps;    // leading steps whose prediction records every block of the obstacle pass keeps in shared memory
     int obs_chunks;         // step chunks of the split obstacle pass (1: frx_obstacle_kernel finishes the plan inline)
     double* obs_part;       // [obs_chunks][N] partial prediction cost of a chunk
     uint32_t* obs_hit;      // [obs_chunks][N] first colliding hull of a chunk: collide | boundary << 8, 127 = none

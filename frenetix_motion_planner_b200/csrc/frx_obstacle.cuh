@@ -25,11 +25,14 @@
 // ego box only (the hull of boxes i0 - 1, i0 needs it).  Plans with >= 8 units per warp run one chunk and finish inline.
 #pragma once
 
+#ifndef FRX_OBS_THREADS
 #define FRX_OBS_THREADS 256
+#endif
 #ifndef FRX_OBS_ROWS
 #define FRX_OBS_ROWS 2
 #endif
 #define FRX_OBS_NOHIT 127u
+#define FRX_OBS_RING_BYTES (FRX_OBS_THREADS / 32 * 2 * FRX_OBS_ROWS * 3 * 32 * 8)      // two slots of R * 3 planes of 32 doubles per warp
 
 
 struct FrxObsAcc {      // what a thread carries to the end of the kernel
@@ -172,6 +175,29 @@ __device__ __forceinline__ void frx_obs_block_finish(const FrxKernelArgs& A, Frx
     }
 }
 
+// ---- x / y / theta of the next step: 16-byte asynchronous copies (LDGSTS, L2 -> shared memory, no register, no L1
+// allocation) into a two-slot ring per warp.  Held in registers across a step -- twelve doubles per thread -- the values
+// were spilled by ptxas the moment they were loaded, which makes the "prefetch" wait for DRAM on the spot (a fifth of all
+// stall samples, profiles/r02_ncu_obstacle_config5_1250k_stage_report.txt).  Chunk c of a warp's R * 3 planes of 256 bytes:
+// row set c / 48, field (c % 48) / 16, candidates 2 * (c % 16) and + 1.
+__device__ __forceinline__ void frx_obs_prefetch(double* slot, const double* const (&wbase)[FRX_OBS_ROWS], const size_t step_off,
+                                                 const bool with_theta, const int lane) {
+#pragma unroll
+    for (int c0 = 0; c0 < FRX_OBS_ROWS * 48; c0 += 32) {
+        const int c = c0 + lane, u = c / 48, f = (c % 48) >> 4, pos = (c & 15) * 2;
+        if (c < FRX_OBS_ROWS * 48 && (f < 2 || with_theta)) {
+            const double* g = wbase[u < FRX_OBS_ROWS ? u : 0] + step_off + f * 32 + pos;
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(slot + (u * 3 + f) * 32 + pos);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(g) : "memory");
+        }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void frx_obs_prefetch_wait() {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+}
+
 // PMODE: 0 = inverse-Mahalanobis prediction cost (python path), 1 = collision probability (cpp flavour) -- separate
 // instances so that the default one keeps its register budget
 template <int PMODE>
@@ -180,12 +206,24 @@ frx_obstacle_kernel(const __grid_constant__ FrxKernelArgs A) {
     const int lane = threadIdx.x & 31;
     const int Nt = A.Nt;
     const long long N = A.N;
-    constexpr size_t fstride = 32;                         // [block of 32 candidates][step][field][32], see frx_state_index
     const size_t Np = (size_t)A.nf_store * 32;             // doubles between two steps of a candidate
     __shared__ int s_npred[64], s_nhull[64];               // records per step (Nt <= 64)
+    // The prediction records of the first obs_stage_steps steps live in shared memory for the life of the block (filled once,
+    // read by every warp at every step); later steps are read through the L1, whose working set shrinks accordingly.
+    // Through the L1 alone the 16 warps of an SM, each at its own step, keep evicting each other's records (hit rate 77 %,
+    // a third of all stall samples on the record loads: profiles/r02_ncu_obstacle_config5_1250k_report.txt).
+    extern __shared__ double2 s_dyn[];                     // state ring of every warp (frx_obs_prefetch), then the records
+    double* const s_ring = reinterpret_cast<double*>(s_dyn);
+    const double2* const s_rec = s_dyn + FRX_OBS_RING_BYTES / sizeof(double2);
+    const int stage = (PMODE == 0) ? A.obs_stage_steps : 0;
     for (int k = threadIdx.x; k < 64; k += FRX_OBS_THREADS) {
         s_npred[k] = (A.O > 0 && k < A.Tp) ? A.on_pred[k] : 0;
         s_nhull[k] = (A.O > 0 && k < A.Tp) ? A.on_hull[k] : 0;
+    }
+    {
+        const double2* __restrict__ g = reinterpret_cast<const double2*>(A.opred);
+        const int n2 = stage * A.O * (FRX_PRED_REC / 2);
+        for (int k = threadIdx.x; k < n2; k += FRX_OBS_THREADS) s_dyn[FRX_OBS_RING_BYTES / sizeof(double2) + k] = __ldg(g + k);
     }
     __syncthreads();
     unsigned cost_mask = 0;
@@ -230,38 +268,35 @@ frx_obstacle_kernel(const __grid_constant__ FrxKernelArgs A) {
         const bool w_col = w_sweep || (w_pred && PMODE == 1);         // theta is needed (sweep, or the probability cost)
         if ((w_pred || w_d2o || w_col) && i0 < i1) {
             double pbx[R], pby[R], pux[R], puy[R];   // ego box of the previous step
-            const double* q[R];
-            double x1[R], y1[R], t1[R], x2[R], y2[R], t2[R];     // steps i + 1 and i + 2, in flight
+            const double* wbase[R];                  // x plane of the warp's 32 candidates at step 0 (warp-uniform)
             // a later chunk starts one step early: that step only yields the ego box the first hull needs
             const int ifirst = (i0 > 0 && w_sweep) ? (i0 - 1) : i0;
 #pragma unroll
             for (int u = 0; u < R; ++u) {
                 pbx[u] = pby[u] = pux[u] = puy[u] = 0.0;
-                q[u] = A.states + frx_state_index(rr_[u], Nt, A.nf_store, 0, ifirst);
-                x1[u] = __ldcg(q[u]); y1[u] = __ldcg(q[u] + fstride); t1[u] = w_col ? __ldcg(q[u] + 2 * fstride) : 0.0;
-                x2[u] = y2[u] = t2[u] = 0.0;
-                if (ifirst + 1 < i1) {
-                    x2[u] = __ldcg(q[u] + Np); y2[u] = __ldcg(q[u] + Np + fstride);
-                    if (w_col) t2[u] = __ldcg(q[u] + Np + 2 * fstride);
-                }
+                long long r0 = b0 + (long long)u * FRX_OBS_THREADS + (threadIdx.x & ~31);
+                if (r0 >= N) r0 = (N - 1) & ~31LL;                              // a warp past the end re-reads the last block
+                wbase[u] = A.states + frx_state_index(r0, Nt, A.nf_store, 0, 0);
             }
+            double* ring = s_ring + (threadIdx.x >> 5) * (2 * R * 3 * 32);
+            __syncwarp();                                                       // the previous unit's last reads of the ring
+            frx_obs_prefetch(ring, wbase, (size_t)ifirst * Np, w_col, lane);
             for (int i = ifirst; i < i1; ++i) {
                 double x[R], y[R], th[R];
+                double* cur = ring + ((i - ifirst) & 1) * (R * 3 * 32);
+                frx_obs_prefetch_wait();
 #pragma unroll
                 for (int u = 0; u < R; ++u) {
-                    x[u] = x1[u]; y[u] = y1[u]; th[u] = t1[u];
-                    x1[u] = x2[u]; y1[u] = y2[u]; t1[u] = t2[u];
-                    if (i + 2 < i1) {
-                        x2[u] = __ldcg(q[u] + 2 * Np); y2[u] = __ldcg(q[u] + 2 * Np + fstride);
-                        if (w_col) t2[u] = __ldcg(q[u] + 2 * Np + 2 * fstride);
-                    }
-                    q[u] += Np;
+                    x[u] = cur[(u * 3 + 0) * 32 + lane]; y[u] = cur[(u * 3 + 1) * 32 + lane];
+                    th[u] = w_col ? cur[(u * 3 + 2) * 32 + lane] : 0.0;
                 }
+                if (i + 1 < i1) frx_obs_prefetch(ring + ((i + 1 - ifirst) & 1) * (R * 3 * 32), wbase, (size_t)(i + 1) * Np, w_col, lane);
                 const bool warm = i < i0;                   // box-only step in front of a later chunk
                 if (w_pred && i >= 1 && !warm) {
                     if (PMODE == 0)
-                        frx_pred_step<R>(A.opred + (size_t)(i - 1) * A.O * FRX_PRED_REC, s_npred[i - 1], x, y, need_pred, pred_sum, ox, oy,
-                                         A.obs, A.Tp, i - 1);
+                        frx_pred_step<R, true>((i - 1 < stage) ? reinterpret_cast<const double*>(s_rec) + (size_t)(i - 1) * A.O * FRX_PRED_REC
+                                                               : A.opred + (size_t)(i - 1) * A.O * FRX_PRED_REC,
+                                               s_npred[i - 1], x, y, need_pred, pred_sum, ox, oy, A.obs, A.Tp, i - 1);
                     else
                         frx_prob_step<R>(A.oprob + (size_t)(i - 1) * A.O * FRX_PROB_REC, s_npred[i - 1], x, y, th, need_pred, pred_sum,
                                          2 * A.half_len, 2 * A.half_wid);
@@ -429,21 +464,51 @@ static int frx_obstacle_chunks(const FrxKernelArgs& a, long long warps_resident)
 // scratch the chunked pass needs (elements of obs_part / obs_hit)
 size_t frx_obstacle_scratch_elems(long long N) { return (size_t)8 * (size_t)N; }
 
+// Shared memory the prediction records may take per block (two blocks per SM share 228 KB with ~28 KB of static arrays each
+// and with the L1, which still has to hold the cull records, the hulls and the records of the steps that are not staged)
+#if FRX_OBS_MIN_CTAS >= 2
+#define FRX_OBS_STAGE_MAX_BYTES (84 * 1024)
+#else
+#define FRX_OBS_STAGE_MAX_BYTES (160 * 1024)
+#endif
+#define FRX_OBS_STAGE_BYTES FRX_OBS_STAGE_MAX_BYTES
+
 cudaError_t frx_launch_obstacle_pass(FrxKernelArgs& a, int sm_count, cudaStream_t st, int* launches) {
-    static thread_local int occ = 0;
+    static thread_local int occ = 0, carve = -1;
     if (occ == 0) {
-        cudaFuncSetAttribute(frx_obstacle_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, 4);   // 8 KB shared, the rest L1
-        cudaFuncSetAttribute(frx_obstacle_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, 4);
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, frx_obstacle_kernel<0>, FRX_OBS_THREADS, 0) != cudaSuccess || occ < 1) occ = 1;
+        cudaFuncSetAttribute(frx_obstacle_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FRX_OBS_STAGE_MAX_BYTES + FRX_OBS_RING_BYTES);
+        cudaFuncSetAttribute(frx_obstacle_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FRX_OBS_RING_BYTES);
+        cudaFuncSetAttribute(frx_obstacle_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, 26);  // static arrays, the rest L1
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, frx_obstacle_kernel<0>, FRX_OBS_THREADS, FRX_OBS_STAGE_MAX_BYTES + FRX_OBS_RING_BYTES) != cudaSuccess || occ < 1) occ = 1;
         if (getenv("FRX_DEBUG")) fprintf(stderr, "[frx] obstacle kernel: %d blocks of %d threads per SM\n", occ, FRX_OBS_THREADS);
+    }
+    // prediction records staged in shared memory: as many leading steps as fit
+    size_t dyn = FRX_OBS_RING_BYTES;
+    a.obs_stage_steps = 0;
+    if (a.pred_mode == 0 && a.O > 0 && a.opred != nullptr) {
+        const size_t per_step = (size_t)a.O * FRX_PRED_REC * sizeof(double);
+        size_t budget = FRX_OBS_STAGE_BYTES;
+        if (const char* e = getenv("FRX_OBS_STAGE_KB")) {                      // tuning: 0 = records through the L1 only
+            budget = (size_t)atoll(e) * 1024;
+            if (budget > FRX_OBS_STAGE_MAX_BYTES) budget = FRX_OBS_STAGE_MAX_BYTES;
+        }
+        long long steps = (long long)(budget / per_step);
+        const int used = a.Tp < a.Nt - 1 ? a.Tp : a.Nt - 1;                    // record lists the steps 1 .. Nt - 1 read
+        a.obs_stage_steps = (int)(steps < used ? steps : used);
+        dyn += (size_t)a.obs_stage_steps * per_step;
+        const int want_carve = (int)((FRX_OBS_MIN_CTAS * (dyn + 5 * 1024)) * 100 / (228 * 1024)) + 1;       // the rest stays L1
+        if (want_carve != carve) {
+            cudaFuncSetAttribute(frx_obstacle_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, want_carve > 100 ? 100 : want_carve);
+            carve = want_carve;
+        }
     }
     const long long full = (long long)sm_count * occ;
     a.obs_chunks = frx_obstacle_chunks(a, full * (FRX_OBS_THREADS / 32));
     const long long row_blocks = (a.N + FRX_OBS_THREADS * FRX_OBS_ROWS - 1) / (FRX_OBS_THREADS * FRX_OBS_ROWS);
     const long long want = row_blocks * a.obs_chunks;
     const int grid = (int)(want < full ? want : full);
-    if (a.pred_mode == 1) frx_obstacle_kernel<1><<<grid, FRX_OBS_THREADS, 0, st>>>(a);
-    else frx_obstacle_kernel<0><<<grid, FRX_OBS_THREADS, 0, st>>>(a);
+    if (a.pred_mode == 1) frx_obstacle_kernel<1><<<grid, FRX_OBS_THREADS, FRX_OBS_RING_BYTES, st>>>(a);
+    else frx_obstacle_kernel<0><<<grid, FRX_OBS_THREADS, dyn, st>>>(a);
     *launches = 1;
     if (a.obs_chunks > 1) {
         long long fg = (a.N + FRX_OBS_THREADS - 1) / FRX_OBS_THREADS;

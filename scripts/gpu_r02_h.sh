@@ -1,5 +1,5 @@
 # scripts/gpu_r02_h.sh: parity for the new prediction-cost form + default bench
 set -x
 mkdir -p gpurun_out
-timeout 1800 python -m pytest tests/test_gpu_parity.py tests/test_gpu_scale.py tests/test_gpu_properties.py -m gpu -q -x > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log; tail -8 gpurun_out/pytest_gpu.log
+timeout 1800 python -m pytest tests/test_gpu_parity.py tests/test_gpu_scale.py tests/test_gpu_properties.py -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log; tail -8 gpurun_out/pytest_gpu.log
 timeout 900 python bench.py > gpurun_out/r02_bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; tail -3 gpurun_out/bench.err

@@ -39,6 +39,9 @@ def load_golden(name):
     return g, ref, prm, preds
 
 
+SINGULAR_V = 1e4        # m/s: beyond this a row sits on the Frenet singularity (see compare_with_oracle)
+
+
 def rel_err(a, b):
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
@@ -164,8 +167,15 @@ def compare_with_oracle(dev, ora, prm, tol=1e-6, check_collide=True, band=BAND, 
     costed = ((fl_o & np.uint64(fo.FLAG_COSTED)) != 0) & ok
     errs = {}
     if dev["states"] is not None:
+        # A candidate that runs into the singularity of the Frenet transform (1 - kappa_r d -> 0, theta_cl -> pi/2: speeds of
+        # 1e10 m/s) amplifies the last-ulp difference between the device's atan and libm's by 1 / cos(theta_cl); it is
+        # infeasible on both sides (the flags above are compared exactly) and only has to be singular on both sides.
+        with np.errstate(invalid="ignore"):
+            singular = np.nanmax(np.abs(ora["states"][fo.F_V]), axis=1) > SINGULAR_V
+            assert np.array_equal(singular[stored], (np.nanmax(np.abs(dev["states"][fo.F_V]), axis=1) > SINGULAR_V)[stored])
+        cmp_rows = stored & ~singular
         for f, name in enumerate(fo.FIELDS):
-            errs[name] = rel_err(dev["states"][f][stored], ora["states"][f][stored])
+            errs[name] = rel_err(dev["states"][f][cmp_rows], ora["states"][f][cmp_rows])
     errs["costs"] = rel_err(dev["costs"][costed], ora["costs"][costed])
     errs["total"] = rel_err(dev["total"][costed], ora["total"][costed])
     worst = max(errs.values()) if errs else 0.0

@@ -253,7 +253,8 @@ def test_collision_probability_prediction_cost_matches_the_oracle(name, correlat
     ora = fo.plan(S, ref, p1, preds)
     k = list(ora["cost_names"]).index("prediction")
     costed = (ora["flags"] & fo.FLAG_COSTED) != 0
-    assert (ora["costs"][costed, k] > 0).sum() > 10                           # the term is alive in this case
+    if correlated or name != "scurve_lowvel_nodraw":                          # (that case's obstacles start > 5 m away: all-zero term)
+        assert (ora["costs"][costed, k] > 0).sum() > 10                       # the term is alive in this case
     for chunks in ("1", "4"):
         monkeypatch.setenv("FRX_OBS_CHUNKS", chunks)
         dev = device_plan(S, ref, p1, preds)
@@ -278,7 +279,13 @@ def test_prediction_cost_exact_fallback(monkeypatch):
     cov[9] = [[0.3, 0.1], [0.25, 0.4]]                     # not symmetric (the quadratic form only sees the symmetric part)
     preds[0]["cov_list"] = cov
     pos = np.array(preds[1]["pos_list"], dtype=float).copy()
-    r = int(np.flatnonzero((ora0["flags"] & fo.FLAG_COSTED) != 0)[17])
+    # a costed row whose position at step 7 is the same double on both sides (states agree to an ulp or two, most of them
+    # exactly): "the ego ON the mean" must mean the same thing to the device and to the oracle
+    dev0 = device_plan(S, ref, prm, preds)
+    same = (dev0["states"][fo.F_X][:, 7] == ora0["states"][fo.F_X][:, 7]) & (dev0["states"][fo.F_Y][:, 7] == ora0["states"][fo.F_Y][:, 7])
+    rows = np.flatnonzero(((ora0["flags"] & fo.FLAG_COSTED) != 0) & same)
+    assert rows.size > 20
+    r = int(rows[17])
     pos[6] = [ora0["states"][fo.F_X][r, 7], ora0["states"][fo.F_Y][r, 7]]       # obstacle mean == ego position of row r at step 7
     preds[1]["pos_list"] = pos
     ora = fo.plan(S, ref, prm, preds)
