@@ -419,7 +419,8 @@ static int prepare_plan(frx_ctx* ctx, long long N, const double* d_sampling, boo
     }
     if (ctx->O > 0 && ctx->compact_Nt != Nt) {        // per-step compact records (depend on the horizon through min(Nt, len))
         const int Tp = ctx->Tp;
-        CK(ctx->opred.reserve((size_t)Tp * ctx->O * 6)); CK(ctx->ohull.reserve((size_t)Tp * ctx->O * 8));
+        CK(ctx->opred.reserve((size_t)Tp * ctx->O * 6 + 2 * 6));   // + 2 records: frx_pred_step reads one half group ahead
+        CK(ctx->ohull.reserve((size_t)Tp * ctx->O * 8));
         CK(ctx->ohull32.reserve((size_t)Tp * ctx->O));
         CK(ctx->on_pred.reserve(Tp)); CK(ctx->on_hull.reserve(Tp));
         frx_launch_obstacle_compact(ctx->O, Tp, Nt, ctx->obs.p, ctx->obs_len.p, ctx->origin_x, ctx->origin_y, ctx->opred.p,

@@ -11,9 +11,6 @@
 #define FRX_MIN_CTAS 2   // resident CTAs per SM the eval kernel is compiled for (register cap 168)
 #endif
 #define FRX_MAX_T_VALUES 128
-#ifndef FRX_OBS_MIN_CTAS
-#define FRX_OBS_MIN_CTAS 2   // resident 256-thread blocks per SM the obstacle kernel is compiled for (register cap 128)
-#endif
 #define FRX_EPS 1e-5
 
 // obstacle table, SoA with step pitch Tp: arr[(o * FRX_OBS_NARR + k) * Tp + t]

@@ -613,7 +613,7 @@ __device__ __forceinline__ FrxLaneOut frx_candidate(const FrxKernelArgs& A, cons
                     const double xs[1] = {x}, ys[1] = {y};
                     const bool nd[1] = {true};
                     double acc[1] = {pred_sum};
-                    frx_pred_step<1>(A.opred + (size_t)(i - 1) * A.O * FRX_PRED_REC, __ldg(A.on_pred + (i - 1)), xs, ys, nd, acc, A.origin_x,
+                    frx_pred_step<1>(reinterpret_cast<const double2*>(A.opred + (size_t)(i - 1) * A.O * FRX_PRED_REC), __ldg(A.on_pred + (i - 1)), xs, ys, nd, acc, A.origin_x,
                                      A.origin_y, A.obs, A.Tp, i - 1);
                     pred_sum = acc[0];
                 }

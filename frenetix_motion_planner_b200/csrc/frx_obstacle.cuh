@@ -32,7 +32,7 @@
 #define FRX_OBS_ROWS 2
 #endif
 #define FRX_OBS_NOHIT 127u
-#define FRX_OBS_RING_BYTES (FRX_OBS_THREADS / 32 * 2 * FRX_OBS_ROWS * 3 * 32 * 8)      // two slots of R * 3 planes of 32 doubles per warp
+#define FRX_OBS_RING_BYTES(threads) ((threads) / 32 * 2 * FRX_OBS_ROWS * 3 * 32 * 8)      // two slots of R * 3 planes of 32 doubles per warp
 
 
 struct FrxObsAcc {      // what a thread carries to the end of the kernel
@@ -74,12 +74,13 @@ __device__ __forceinline__ void frx_obs_row_finish(const FrxKernelArgs& A, const
 // block reduction of (min cost, lowest row) and the two counters of this pass; the last block finishes the plan: winners
 // of all blocks, counter rows of the eval kernel's CTAs (A.n_cta of them) plus this pass's two global counters, result
 // record + winner state rows to mapped host memory
+template <int THREADS>
 __device__ __forceinline__ void frx_obs_block_finish(const FrxKernelArgs& A, FrxObsAcc acc) {
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    constexpr int NW = FRX_OBS_THREADS / 32;
+    constexpr int NW = THREADS / 32;
     __shared__ FrxBest s_best[NW];
     __shared__ unsigned int s_hits[2];
-    __shared__ unsigned long long s_part[FRX_OBS_THREADS];
+    __shared__ unsigned long long s_part[THREADS];
     __shared__ int s_is_last;
     if (threadIdx.x < 2) s_hits[threadIdx.x] = 0u;
     __syncthreads();
@@ -116,9 +117,9 @@ __device__ __forceinline__ void frx_obs_block_finish(const FrxKernelArgs& A, Frx
     if (!s_is_last) return;
     __threadfence();
     constexpr int NC = CNT_REASON1 + 10;
-    constexpr int NPART = FRX_OBS_THREADS / NC;
+    constexpr int NPART = THREADS / NC;
     FrxBest b; b.cost = __longlong_as_double(0x7ff0000000000000LL); b.idx = -1;
-    for (int k = threadIdx.x; k < (int)gridDim.x; k += FRX_OBS_THREADS) {
+    for (int k = threadIdx.x; k < (int)gridDim.x; k += THREADS) {
         FrxBest o;
         o.cost = __ldcg(&A.blockbest[k].cost);
         o.idx = __ldcg(&A.blockbest[k].idx);
@@ -168,7 +169,7 @@ __device__ __forceinline__ void frx_obs_block_finish(const FrxKernelArgs& A, Frx
     const long long wi = s_best[0].idx;
     const int Nt = A.Nt;
     if (wi >= 0 && A.store_states) {
-        for (int q = threadIdx.x; q < FRX_NUM_FIELDS * Nt; q += FRX_OBS_THREADS) {
+        for (int q = threadIdx.x; q < FRX_NUM_FIELDS * Nt; q += THREADS) {
             const int f = q / Nt, i = q - f * Nt;
             A.host_res->winner_states[f][i] = __ldcg(A.states + frx_state_index(wi, Nt, FRX_NUM_FIELDS, f, i));
         }
@@ -200,8 +201,8 @@ __device__ __forceinline__ void frx_obs_prefetch_wait() {
 
 // PMODE: 0 = inverse-Mahalanobis prediction cost (python path), 1 = collision probability (cpp flavour) -- separate
 // instances so that the default one keeps its register budget
-template <int PMODE>
-__global__ void __launch_bounds__(FRX_OBS_THREADS, FRX_OBS_MIN_CTAS)
+template <int PMODE, int THREADS>
+__global__ void __launch_bounds__(THREADS, 512 / THREADS)
 frx_obstacle_kernel(const __grid_constant__ FrxKernelArgs A) {
     const int lane = threadIdx.x & 31;
     const int Nt = A.Nt;
@@ -214,16 +215,15 @@ frx_obstacle_kernel(const __grid_constant__ FrxKernelArgs A) {
     // a third of all stall samples on the record loads: profiles/r02_ncu_obstacle_config5_1250k_report.txt).
     extern __shared__ double2 s_dyn[];                     // state ring of every warp (frx_obs_prefetch), then the records
     double* const s_ring = reinterpret_cast<double*>(s_dyn);
-    const double2* const s_rec = s_dyn + FRX_OBS_RING_BYTES / sizeof(double2);
     const int stage = (PMODE == 0) ? A.obs_stage_steps : 0;
-    for (int k = threadIdx.x; k < 64; k += FRX_OBS_THREADS) {
+    for (int k = threadIdx.x; k < 64; k += THREADS) {
         s_npred[k] = (A.O > 0 && k < A.Tp) ? A.on_pred[k] : 0;
         s_nhull[k] = (A.O > 0 && k < A.Tp) ? A.on_hull[k] : 0;
     }
     {
         const double2* __restrict__ g = reinterpret_cast<const double2*>(A.opred);
-        const int n2 = stage * A.O * (FRX_PRED_REC / 2);
-        for (int k = threadIdx.x; k < n2; k += FRX_OBS_THREADS) s_dyn[FRX_OBS_RING_BYTES / sizeof(double2) + k] = __ldg(g + k);
+        const int n2 = stage > 0 ? stage * A.O * (FRX_PRED_REC / 2) + FRX_PRED_REC : 0;    // + 2 records: read-ahead of the last group
+        for (int k = threadIdx.x; k < n2; k += THREADS) s_dyn[FRX_OBS_RING_BYTES(THREADS) / sizeof(double2) + k] = __ldg(g + k);
     }
     __syncthreads();
     unsigned cost_mask = 0;
@@ -237,11 +237,11 @@ frx_obstacle_kernel(const __grid_constant__ FrxKernelArgs A) {
     constexpr int R = FRX_OBS_ROWS;
     const int C = A.obs_chunks;                            // step chunks (1: finish inline)
     const int clen = (Nt + C - 1) / C;
-    const long long row_blocks = (N + (long long)R * FRX_OBS_THREADS - 1) / ((long long)R * FRX_OBS_THREADS);
+    const long long row_blocks = (N + (long long)R * THREADS - 1) / ((long long)R * THREADS);
     const long long n_units = row_blocks * C;
     // the trip count is uniform over the block: every warp-synchronous step below is reached by all 32 lanes
     for (long long unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-        const long long b0 = (unit / C) * R * FRX_OBS_THREADS;
+        const long long b0 = (unit / C) * R * THREADS;
         const int chunk = (int)(unit % C);
         const int i0 = chunk * clen, i1 = (i0 + clen < Nt) ? (i0 + clen) : Nt;
         long long rr_[R];
@@ -250,7 +250,7 @@ frx_obstacle_kernel(const __grid_constant__ FrxKernelArgs A) {
         bool any_pred = false, any_col = false, any_d2o = false;
 #pragma unroll
         for (int u = 0; u < R; ++u) {
-            const long long r = b0 + (long long)u * FRX_OBS_THREADS + threadIdx.x;
+            const long long r = b0 + (long long)u * THREADS + threadIdx.x;
             live[u] = r < N;
             rr_[u] = live[u] ? r : (N - 1);
             fl[u] = live[u] ? A.flags[rr_[u]] : 0u;
@@ -274,7 +274,7 @@ frx_obstacle_kernel(const __grid_constant__ FrxKernelArgs A) {
 #pragma unroll
             for (int u = 0; u < R; ++u) {
                 pbx[u] = pby[u] = pux[u] = puy[u] = 0.0;
-                long long r0 = b0 + (long long)u * FRX_OBS_THREADS + (threadIdx.x & ~31);
+                long long r0 = b0 + (long long)u * THREADS + (threadIdx.x & ~31);
                 if (r0 >= N) r0 = (N - 1) & ~31LL;                              // a warp past the end re-reads the last block
                 wbase[u] = A.states + frx_state_index(r0, Nt, A.nf_store, 0, 0);
             }
@@ -293,10 +293,12 @@ frx_obstacle_kernel(const __grid_constant__ FrxKernelArgs A) {
                 if (i + 1 < i1) frx_obs_prefetch(ring + ((i + 1 - ifirst) & 1) * (R * 3 * 32), wbase, (size_t)(i + 1) * Np, w_col, lane);
                 const bool warm = i < i0;                   // box-only step in front of a later chunk
                 if (w_pred && i >= 1 && !warm) {
-                    if (PMODE == 0)
-                        frx_pred_step<R, true>((i - 1 < stage) ? reinterpret_cast<const double*>(s_rec) + (size_t)(i - 1) * A.O * FRX_PRED_REC
-                                                               : A.opred + (size_t)(i - 1) * A.O * FRX_PRED_REC,
-                                               s_npred[i - 1], x, y, need_pred, pred_sum, ox, oy, A.obs, A.Tp, i - 1);
+                    if (PMODE == 0 && i - 1 < stage)
+                        frx_pred_step<R, FRX_REC_SHARED>(s_dyn + FRX_OBS_RING_BYTES(THREADS) / sizeof(double2) + (size_t)(i - 1) * A.O * (FRX_PRED_REC / 2),
+                                                         s_npred[i - 1], x, y, need_pred, pred_sum, ox, oy, A.obs, A.Tp, i - 1);
+                    else if (PMODE == 0)
+                        frx_pred_step<R, FRX_REC_GLOBAL>(reinterpret_cast<const double2*>(A.opred + (size_t)(i - 1) * A.O * FRX_PRED_REC),
+                                                         s_npred[i - 1], x, y, need_pred, pred_sum, ox, oy, A.obs, A.Tp, i - 1);
                     else
                         frx_prob_step<R>(A.oprob + (size_t)(i - 1) * A.O * FRX_PROB_REC, s_npred[i - 1], x, y, th, need_pred, pred_sum,
                                          2 * A.half_len, 2 * A.half_wid);
@@ -415,7 +417,7 @@ frx_obstacle_kernel(const __grid_constant__ FrxKernelArgs A) {
             }
         }
     }
-    if (C == 1) frx_obs_block_finish(A, acc);
+    if (C == 1) frx_obs_block_finish<THREADS>(A, acc);
 }
 
 // chunked plans: add the partial sums up in chunk order, earliest hit over the chunks, then the same finish as the
@@ -442,7 +444,7 @@ frx_obstacle_finish_kernel(const __grid_constant__ FrxKernelArgs A) {
         frx_obs_row_finish(A, r, fl, (fl & FRX_FLAG_COSTED) && pred_on, pred, 0.0, ck != FRX_OBS_NOHIT, (int)ck, bk != FRX_OBS_NOHIT,
                            (int)bk, acc);
     }
-    frx_obs_block_finish(A, acc);
+    frx_obs_block_finish<FRX_OBS_THREADS>(A, acc);
 }
 
 // How many step chunks: enough units for >= 4 per resident warp, at least 4 steps per chunk; FRX_OBS_CHUNKS overrides
@@ -464,51 +466,36 @@ static int frx_obstacle_chunks(const FrxKernelArgs& a, long long warps_resident)
 // scratch the chunked pass needs (elements of obs_part / obs_hit)
 size_t frx_obstacle_scratch_elems(long long N) { return (size_t)8 * (size_t)N; }
 
-// Shared memory the prediction records may take per block (two blocks per SM share 228 KB with ~28 KB of static arrays each
-// and with the L1, which still has to hold the cull records, the hulls and the records of the steps that are not staged)
-#if FRX_OBS_MIN_CTAS >= 2
-#define FRX_OBS_STAGE_MAX_BYTES (84 * 1024)
-#else
-#define FRX_OBS_STAGE_MAX_BYTES (160 * 1024)
-#endif
-#define FRX_OBS_STAGE_BYTES FRX_OBS_STAGE_MAX_BYTES
+// Two block shapes, 16 warps per SM at 128 registers either way: two blocks of 256 threads when the prediction records of
+// the whole plan fit twice into the SM's shared memory next to the state rings (84 KB each), else one block of 512 threads
+// with up to 160 KB of records (measured, configs[4]: 50 obstacles x 50 steps = 120 KB, 21.2 ms against 23.6 ms with 35 of
+// the 50 steps staged per 256-thread block; configs[2]: 29 KB, 0.238 ms against 0.252 ms the other way round).  What does
+// not fit is read through what is left of the L1.
+#define FRX_OBS_STAGE_BYTES_2 (84 * 1024)
+#define FRX_OBS_STAGE_BYTES_1 (160 * 1024)
 
-cudaError_t frx_launch_obstacle_pass(FrxKernelArgs& a, int sm_count, cudaStream_t st, int* launches) {
+template <int PMODE, int THREADS>
+static cudaError_t frx_launch_obstacle_shape(FrxKernelArgs& a, int sm_count, size_t stage_bytes, cudaStream_t st, int* launches) {
     static thread_local int occ = 0, carve = -1;
+    constexpr size_t RING = FRX_OBS_RING_BYTES(THREADS);
+    constexpr size_t MAXDYN = RING + (PMODE == 0 ? (THREADS == 256 ? FRX_OBS_STAGE_BYTES_2 : FRX_OBS_STAGE_BYTES_1) : 0);
     if (occ == 0) {
-        cudaFuncSetAttribute(frx_obstacle_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FRX_OBS_STAGE_MAX_BYTES + FRX_OBS_RING_BYTES);
-        cudaFuncSetAttribute(frx_obstacle_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FRX_OBS_RING_BYTES);
-        cudaFuncSetAttribute(frx_obstacle_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, 26);  // static arrays, the rest L1
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, frx_obstacle_kernel<0>, FRX_OBS_THREADS, FRX_OBS_STAGE_MAX_BYTES + FRX_OBS_RING_BYTES) != cudaSuccess || occ < 1) occ = 1;
-        if (getenv("FRX_DEBUG")) fprintf(stderr, "[frx] obstacle kernel: %d blocks of %d threads per SM\n", occ, FRX_OBS_THREADS);
+        cudaFuncSetAttribute(frx_obstacle_kernel<PMODE, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MAXDYN);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, frx_obstacle_kernel<PMODE, THREADS>, THREADS, MAXDYN) != cudaSuccess || occ < 1) occ = 1;
+        if (getenv("FRX_DEBUG")) fprintf(stderr, "[frx] obstacle kernel<%d>: %d blocks of %d threads per SM\n", PMODE, occ, THREADS);
     }
-    // prediction records staged in shared memory: as many leading steps as fit
-    size_t dyn = FRX_OBS_RING_BYTES;
-    a.obs_stage_steps = 0;
-    if (a.pred_mode == 0 && a.O > 0 && a.opred != nullptr) {
-        const size_t per_step = (size_t)a.O * FRX_PRED_REC * sizeof(double);
-        size_t budget = FRX_OBS_STAGE_BYTES;
-        if (const char* e = getenv("FRX_OBS_STAGE_KB")) {                      // tuning: 0 = records through the L1 only
-            budget = (size_t)atoll(e) * 1024;
-            if (budget > FRX_OBS_STAGE_MAX_BYTES) budget = FRX_OBS_STAGE_MAX_BYTES;
-        }
-        long long steps = (long long)(budget / per_step);
-        const int used = a.Tp < a.Nt - 1 ? a.Tp : a.Nt - 1;                    // record lists the steps 1 .. Nt - 1 read
-        a.obs_stage_steps = (int)(steps < used ? steps : used);
-        dyn += (size_t)a.obs_stage_steps * per_step;
-        const int want_carve = (int)((FRX_OBS_MIN_CTAS * (dyn + 5 * 1024)) * 100 / (228 * 1024)) + 1;       // the rest stays L1
-        if (want_carve != carve) {
-            cudaFuncSetAttribute(frx_obstacle_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, want_carve > 100 ? 100 : want_carve);
-            carve = want_carve;
-        }
+    const size_t dyn = RING + stage_bytes;
+    const int want_carve = (int)(((512 / THREADS) * (dyn + 5 * 1024)) * 100 / (228 * 1024)) + 1;       // the rest stays L1
+    if (want_carve != carve) {
+        cudaFuncSetAttribute(frx_obstacle_kernel<PMODE, THREADS>, cudaFuncAttributePreferredSharedMemoryCarveout, want_carve > 100 ? 100 : want_carve);
+        carve = want_carve;
     }
     const long long full = (long long)sm_count * occ;
-    a.obs_chunks = frx_obstacle_chunks(a, full * (FRX_OBS_THREADS / 32));
-    const long long row_blocks = (a.N + FRX_OBS_THREADS * FRX_OBS_ROWS - 1) / (FRX_OBS_THREADS * FRX_OBS_ROWS);
+    a.obs_chunks = frx_obstacle_chunks(a, full * (THREADS / 32));
+    const long long row_blocks = (a.N + THREADS * FRX_OBS_ROWS - 1) / (THREADS * FRX_OBS_ROWS);
     const long long want = row_blocks * a.obs_chunks;
     const int grid = (int)(want < full ? want : full);
-    if (a.pred_mode == 1) frx_obstacle_kernel<1><<<grid, FRX_OBS_THREADS, FRX_OBS_RING_BYTES, st>>>(a);
-    else frx_obstacle_kernel<0><<<grid, FRX_OBS_THREADS, dyn, st>>>(a);
+    frx_obstacle_kernel<PMODE, THREADS><<<grid, THREADS, dyn, st>>>(a);
     *launches = 1;
     if (a.obs_chunks > 1) {
         long long fg = (a.N + FRX_OBS_THREADS - 1) / FRX_OBS_THREADS;
@@ -517,6 +504,30 @@ cudaError_t frx_launch_obstacle_pass(FrxKernelArgs& a, int sm_count, cudaStream_
         *launches = 2;
     }
     return cudaGetLastError();
+}
+
+cudaError_t frx_launch_obstacle_pass(FrxKernelArgs& a, int sm_count, cudaStream_t st, int* launches) {
+    a.obs_stage_steps = 0;
+    if (a.pred_mode == 1) return frx_launch_obstacle_shape<1, 256>(a, sm_count, 0, st, launches);
+    // prediction records staged in shared memory: as many leading steps as fit
+    bool wide = false;
+    size_t per_step = 0;
+    if (a.O > 0 && a.opred != nullptr) {
+        per_step = (size_t)a.O * FRX_PRED_REC * sizeof(double);
+        const int used = a.Tp < a.Nt - 1 ? a.Tp : a.Nt - 1;                    // record lists the steps 1 .. Nt - 1 read
+        wide = (size_t)used * per_step > FRX_OBS_STAGE_BYTES_2;
+        if (const char* e = getenv("FRX_OBS_WIDE")) wide = atoi(e) != 0;       // tuning: force a shape
+        size_t budget = wide ? FRX_OBS_STAGE_BYTES_1 : FRX_OBS_STAGE_BYTES_2;
+        if (const char* e = getenv("FRX_OBS_STAGE_KB")) {                      // tuning: 0 = records through the L1 only
+            const size_t b = (size_t)atoll(e) * 1024;
+            if (b < budget) budget = b;
+        }
+        const long long steps = budget > 96 ? (long long)((budget - 96) / per_step) : 0;
+        a.obs_stage_steps = (int)(steps < used ? steps : used);
+    }
+    const size_t stage_bytes = a.obs_stage_steps > 0 ? (size_t)a.obs_stage_steps * per_step + 2 * FRX_PRED_REC * sizeof(double) : 0;
+    return wide ? frx_launch_obstacle_shape<0, 512>(a, sm_count, stage_bytes, st, launches)
+                : frx_launch_obstacle_shape<0, 256>(a, sm_count, stage_bytes, st, launches);
 }
 int frx_obstacle_pass_max_grid(int sm_count) { return sm_count * 8; }
 
