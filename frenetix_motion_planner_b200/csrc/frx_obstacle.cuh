@@ -4,11 +4,13 @@
 //
 // Why split from the eval kernel: this pass is pure fp64 arithmetic on warp-uniform obstacle records.  Inside the eval
 // kernel it runs at 12 warps per SM (168 registers, 175 KB of shared memory per SM, ~50 KB of L1 left for the records);
-// here it needs almost no shared memory (the records live in a ~200 KB L1) and runs 16 warps per SM at 128 registers.
+// here it runs 16 warps per SM at 128 registers with the records in shared memory.
 //
-// Work unit = (64 candidates per warp: rows r and r + 256 of a thread, a CHUNK of the time steps).  One thread per
-// candidate, x / y / theta come back from the state planes, coalesced, loaded TWO steps ahead of their use.  Per step:
-//   * prediction cost: frx_pred_step -- 11 fp64 instructions per (candidate, obstacle) instead of 20;
+// Work unit = (64 or 128 candidates per warp pair of rows: rows r and r + THREADS of a thread, a CHUNK of the time steps).
+// One thread per candidate; x / y / theta come back from the state planes through a cp.async ring, one step ahead.
+// Per step:
+//   * prediction cost: frx_pred_step -- 9.25 fp64 instructions per (candidate, obstacle) instead of 20, records read with
+//     LDS from the block's staged copy (DESIGN.md section 5 for what was measured on the way);
 //   * collision: every lane builds its exact ego hull (obb-sum of boxes k, k + 1); the warp then culls the step's
 //     obstacle hulls COOPERATIVELY: the bounding box of the 32 ego hull circles comes from four REDUX min/max on
 //     order-preserving integer images of fp32 coordinates, lane o tests obstacle o against it (fp32, conservatively
