@@ -28,6 +28,7 @@ enum {
     CNT_T_NOT_FOUND,
     CNT_WORK,          // chunk ticket counter of the eval kernel's dynamic scheduler
     CNT_DONE,          // CTAs of this plan that have finished (last one publishes the result)
+    CNT_OBS_WORK,      // unit ticket counter of the obstacle kernel's warps
     FRX_NUM_COUNTERS
 };
 

@@ -152,6 +152,56 @@ def test_split_obstacle_kernel_equals_fused_pass(name, monkeypatch):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("n_obs", [7, 37, 70])
+def test_obstacle_block_shapes_and_record_staging_are_bit_identical(n_obs, monkeypatch):
+    """The split obstacle pass keeps the prediction records of the leading steps in shared memory and runs in one of two
+    block shapes (frx_obstacle.cuh), its units dealt to blocks round-robin or to warps by ticket; which shape, which
+    dealing, and how many steps are staged (all, some, none -- the rest is read through the L1), must not change a
+    single bit.  7 / 37 / 70 obstacles: record lists with every tail length of the
+    four-record groups and more obstacles than the 32 lanes of the cooperative cull; the oracle contract holds."""
+    from frenetix_motion_planner_b200 import synthetic as syn
+    g, ref, prm, _ = load_golden("arc_hv_draw_pred")
+    S = np.ascontiguousarray(np.tile(g["sampling"], (4, 1))[:g["sampling"].shape[0] * 3 + 11])
+    preds = syn.synthetic_predictions(g["polyline"], n_obs, 31, 0.1, seed=77 + n_obs, lateral_spread=20.0)   # some collide, most do not
+    for o, p in enumerate(preds):                      # ragged prediction horizons: per-step lists of different lengths
+        keep = 31 - (o % 5) * 4
+        for key in ("pos_list", "cov_list", "orientation_list", "v_list"):
+            if key in p:
+                p[key] = np.asarray(p[key])[:keep]
+    walls = np.array([[float(np.mean(ref.ref_x[:40])), float(np.mean(ref.ref_y[:40])) + 6.0, 0.3, 30.0, 0.1]])
+    monkeypatch.setenv("FRX_SEG", "1")
+    monkeypatch.setenv("FRX_SPLIT_OBS", "1")
+    monkeypatch.setenv("FRX_OBS_CHUNKS", "1")
+    base = None
+    for wide, stage_kb, ticket in (("0", None, "1"), ("0", "0", "0"), ("0", "4", "1"), ("0", None, "0"), ("1", None, "0"),
+                                   ("1", "0", "1"), ("1", "9", "0"), ("1", None, "1")):
+        monkeypatch.setenv("FRX_OBS_WIDE", wide)
+        monkeypatch.setenv("FRX_OBS_TICKET", ticket)      # units dealt to warps by ticket / to blocks round-robin
+        if stage_kb is None:
+            monkeypatch.delenv("FRX_OBS_STAGE_KB", raising=False)
+        else:
+            monkeypatch.setenv("FRX_OBS_STAGE_KB", stage_kb)
+        dev = device_plan(S, ref, prm, preds, static_obbs=walls)
+        assert dev["res"].obstacle_kernel_ms > 0
+        if base is None:
+            base = dev
+            ora = fo.plan(S, ref, prm, preds, static_obbs=walls)
+            compare_with_oracle(dev, ora, prm, alts=band_alternatives(S, ref, prm, preds, np.flatnonzero(ora["margins"] < BAND), static_obbs=walls))
+            continue
+        for k in ("flags", "traj_len", "costs", "total", "states", "reason_counts"):
+            assert np.array_equal(base[k], dev[k]), (k, wide, stage_kb, ticket)
+        for k in ("argmin", "min_cost", "n_in_list", "n_feasible", "collision_counter"):
+            assert base[k] == dev[k], (k, wide, stage_kb, ticket)
+    monkeypatch.setenv("FRX_SPLIT_OBS", "0")          # and the fused pass of the eval kernel: same operations, same order
+    monkeypatch.delenv("FRX_OBS_WIDE", raising=False)
+    monkeypatch.delenv("FRX_OBS_TICKET", raising=False)
+    monkeypatch.delenv("FRX_OBS_STAGE_KB", raising=False)
+    fused = device_plan(S, ref, prm, preds, static_obbs=walls)
+    for k in ("flags", "traj_len", "costs", "total", "states", "reason_counts"):
+        assert np.array_equal(base[k], fused[k]), k
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("chunks", [2, 4, 8])
 @pytest.mark.parametrize("name", ["arc_hv_draw_pred", "tjunction_draw", "tjunction_nodraw"])
 def test_step_chunked_obstacle_pass(name, chunks, monkeypatch):
