@@ -717,9 +717,9 @@ def run_gpu_workload(env: Env, name: str, steps: int, warmup: int, cpu_baseline:
                         "kernel": "frx_obstacle_kernel", "kernel_ms": obs_mean_ms,
                         "algorithmic_flops_per_candidate": F_cand,
                         "peak_source": "measured live (frx_selftest_fp64_peak: independent DFMA streams on every SM, 2 flop per FMA)",
-                        "note": "fp64-bound, not HBM-bound: 12 flop per (candidate, step, obstacle) + 60 per (candidate, step); a "
-                                "reciprocal counted as 1 flop costs 4 DFMA issue slots and unfused multiplies / adds count 1 flop "
-                                "per slot, so ~0.55 is the ceiling of this fraction (DESIGN.md section 5)"}
+                        "note": "fp64-bound, not HBM-bound: 12 flop per (candidate, step, obstacle) + 60 per (candidate, step); the "
+                                "kernel spends 9.25 fp64 issue slots on those 12 flop and the peak counts 2 flop per slot, so "
+                                "12 / 18.5 = 0.65 is the ceiling of this fraction (DESIGN.md section 5)"}
         # the dominant kernel of the step carries the `roofline` key, the other one rides along
         dominant_obs = roof_obs is not None and obs_mean_ms > eval_mean_ms
         line = {
