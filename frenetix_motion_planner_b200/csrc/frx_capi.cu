@@ -72,6 +72,8 @@ struct frx_ctx {
     cudaStream_t stream = nullptr, own_stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr, evkm = nullptr;
     bool split_last = false;           // the last plan ran the obstacle pass as its own kernel (evkm lies between the two)
+    bool counted_last = false;         // the last plan ran frx_collision_counter_kernel (else its result record still holds
+                                       // the count the PREVIOUS plan left in the device counter: report 0)
     std::string err;
     int sm_count = 148;
     int max_smem_optin = 0;
@@ -496,7 +498,8 @@ static int prepare_plan(frx_ctx* ctx, long long N, const double* d_sampling, boo
 static int enqueue_finish(frx_ctx* ctx, long long N, long long row_base, int grid, cudaStream_t st) {
     (void)grid;
     const frx_params& p = ctx->prm;
-    if (p.check_collisions && (ctx->O > 0 || ctx->B > 0)) {
+    ctx->counted_last = p.check_collisions && (ctx->O > 0 || ctx->B > 0);
+    if (ctx->counted_last) {
         ctx->last_launches += 1;
         long long cg = (N + 255) / 256;
         if (cg > (long long)ctx->sm_count * 4) cg = (long long)ctx->sm_count * 4;
@@ -523,7 +526,7 @@ static int fill_result(frx_ctx* ctx, long long N, frx_result* out) {
     out->n_candidates = (int64_t)h.counters[CNT_CANDIDATES];
     out->n_collide = (int64_t)h.counters[CNT_COLLIDE];
     out->n_boundary = (int64_t)h.counters[CNT_BOUNDARY];
-    out->collision_counter = (int64_t)h.counters[CNT_COLLISION_COUNTER];
+    out->collision_counter = ctx->counted_last ? (int64_t)h.counters[CNT_COLLISION_COUNTER] : 0;
     out->reason_counts[0] = (int64_t)h.counters[CNT_INFEASIBLE_IN_LIST];
     for (int q = 1; q <= 10; ++q) out->reason_counts[q] = (int64_t)h.counters[CNT_REASON1 + q - 1];
     return FRX_OK;

@@ -152,6 +152,35 @@ def test_split_obstacle_kernel_equals_fused_pass(name, monkeypatch):
 
 
 @pytest.mark.gpu
+def test_counters_of_a_plan_do_not_leak_into_the_next_one():
+    """One handler, three plans: with colliding obstacles, without any obstacle, with the obstacles again.  The device
+    keeps Planner._collision_counter in a global counter that the NEXT plan's last block snapshots and clears; a plan that
+    runs no collision pass must report 0, not what its predecessor left there (found by the hypothesis suite)."""
+    from frenetix_motion_planner_b200 import _capi
+    g, ref, prm, preds = load_golden("tjunction_draw")
+    S = g["sampling"]
+    h = _capi.Handler(0)
+    free = fo.plan(S, ref, prm, [])
+    w = free["argmin"]
+    crowded = [dict(p) for p in preds]
+    n = len(crowded[0]["pos_list"])                      # one predicted car drives onto the unobstructed winner from step 18 on
+    pos = np.stack([free["states"][fo.F_X][w, :n], free["states"][fo.F_Y][w, :n]], axis=1)
+    pos[:18] = pos[18] + np.array([0.0, 300.0])
+    crowded[0]["pos_list"] = pos
+    ora = fo.plan(S, ref, prm, crowded)
+    assert ora["collision_counter"] > 0 and ora["argmin"] >= 0 and ora["argmin"] != w
+    n_band = int((ora["margins"] < BAND).sum())         # rows on the stand-still tie may legally fall either way (helpers.py)
+    first = device_plan(S, ref, prm, crowded, handler=h)
+    assert first["collision_counter"] > 0 and abs(first["collision_counter"] - ora["collision_counter"]) <= n_band
+    empty = device_plan(S, ref, prm, [], handler=h)
+    assert empty["collision_counter"] == 0 and empty["res"].n_collide == 0 and empty["res"].n_boundary == 0
+    again = device_plan(S, ref, prm, crowded, handler=h)
+    for k in ("argmin", "min_cost", "n_in_list", "n_feasible", "collision_counter"):
+        assert again[k] == first[k], k
+    assert np.array_equal(again["flags"], first["flags"]) and np.array_equal(again["reason_counts"], first["reason_counts"])
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("n_obs", [7, 37, 70])
 def test_obstacle_block_shapes_and_record_staging_are_bit_identical(n_obs, monkeypatch):
     """The split obstacle pass keeps the prediction records of the leading steps in shared memory and runs in one of two
