@@ -11,8 +11,18 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>       // header-only; a no-op unless a tool (ncu --nvtx, Nsight Systems) is attached
+
 #include "frx.h"
 #include "frx_device.cuh"
+
+// NVTX range over a phase of a C-ABI call: set-up, enqueue (copies + launches), wait (stream sync + result record)
+struct FrxRange {
+    explicit FrxRange(const char* name) { nvtxRangePushA(name); }
+    ~FrxRange() { nvtxRangePop(); }
+    FrxRange(const FrxRange&) = delete;
+    FrxRange& operator=(const FrxRange&) = delete;
+};
 
 // launchers implemented in frx_kernels.cu
 size_t frx_eval_smem_bytes(int Mpad, int Nt);
@@ -558,6 +568,7 @@ static int choose_obstacle_split(frx_ctx* ctx, FrxKernelArgs* a, int grid) {
 static int enqueue_plan(frx_ctx* ctx, long long N, const double* d_sampling, bool grid_mode, int g_nv, int g_nd,
                         const double* d_t1, const double* d_v1, const double* d_d1, const double* xcl,
                         long long row_first, long long row_base) {
+    FrxRange range("frx:enqueue");
     cudaStream_t st = ctx->stream;
     FrxKernelArgs a;
     int grid = 1, Nt = 1;
@@ -604,6 +615,7 @@ static int enqueue_plan(frx_ctx* ctx, long long N, const double* d_sampling, boo
 }
 
 static int wait_plan(frx_ctx* ctx, frx_result* out) {
+    FrxRange range("frx:wait");
     REQUIRE(out != nullptr, "frx_plan: null result");
     REQUIRE(ctx->pending, "frx_plan_wait: no plan in flight");
     CK(cudaStreamSynchronize(ctx->stream));
@@ -642,6 +654,7 @@ static const double* zero_copy_pointer(const double* host) {
 
 int frx_plan(frx_ctx* ctx, int64_t N, const double* sampling, int64_t row_index_base, frx_result* out) {
     if (!ctx) return FRX_ERR_INVALID;
+    FrxRange range("frx_plan");
     REQUIRE(N >= 1 && sampling != nullptr, "frx_plan: empty sampling matrix");
     CK(cudaSetDevice(ctx->device));
     if (const double* mapped = zero_copy_pointer(sampling)) {
@@ -656,6 +669,7 @@ int frx_plan(frx_ctx* ctx, int64_t N, const double* sampling, int64_t row_index_
 
 int frx_plan_device(frx_ctx* ctx, int64_t N, const void* d_sampling, int64_t row_index_base, frx_result* out) {
     if (!ctx) return FRX_ERR_INVALID;
+    FrxRange range("frx_plan_device");
     REQUIRE(N >= 1 && d_sampling != nullptr, "frx_plan_device: empty sampling matrix");
     CK(cudaSetDevice(ctx->device));
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
@@ -664,6 +678,7 @@ int frx_plan_device(frx_ctx* ctx, int64_t N, const void* d_sampling, int64_t row
 
 int frx_plan_device_async(frx_ctx* ctx, int64_t N, const void* d_sampling, int64_t row_index_base) {
     if (!ctx) return FRX_ERR_INVALID;
+    FrxRange range("frx_plan_device_async");
     REQUIRE(N >= 1 && d_sampling != nullptr, "frx_plan_device_async: empty sampling matrix");
     CK(cudaSetDevice(ctx->device));
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
@@ -679,6 +694,7 @@ int frx_plan_wait(frx_ctx* ctx, frx_result* out) {
 int frx_plan_grid(frx_ctx* ctx, int32_t nt, const double* t1, int32_t nv, const double* ss1, int32_t nd,
                   const double* d1, const double* x_cl, int64_t row_first, int64_t row_count, frx_result* out) {
     if (!ctx) return FRX_ERR_INVALID;
+    FrxRange range("frx_plan_grid");
     REQUIRE(nt >= 1 && nv >= 1 && nd >= 1 && t1 && ss1 && d1 && x_cl, "frx_plan_grid: bad arguments");
     const long long total = (long long)nt * nv * nd;
     REQUIRE(row_first >= 0 && row_count >= 1 && row_first + row_count <= total, "frx_plan_grid: row range outside the grid");
@@ -705,6 +721,7 @@ int frx_plan_grid(frx_ctx* ctx, int32_t nt, const double* t1, int32_t nv, const 
 int frx_plan_batched(int32_t n_agents, frx_ctx** ctxs, const int64_t* n_rows, const double* const* samplings,
                      frx_result* results) {
     if (n_agents < 1 || !ctxs || !n_rows || !samplings || !results || !ctxs[0]) return FRX_ERR_INVALID;
+    FrxRange range("frx_plan_batched");
     frx_ctx* ctx = ctxs[0];                       // the batch runs on the first context's stream
     REQUIRE(n_agents <= 256, "frx_plan_batched: at most 256 agents per launch");
     CK(cudaSetDevice(ctx->device));
