@@ -6,7 +6,8 @@
 // kernel it runs at 12 warps per SM (168 registers, 175 KB of shared memory per SM, ~50 KB of L1 left for the records);
 // here it runs 16 warps per SM at 128 registers with the records in shared memory.
 //
-// Work unit = (64 or 128 candidates per warp pair of rows: rows r and r + THREADS of a thread, a CHUNK of the time steps).
+// Work unit = (R = 2 candidates per thread, a CHUNK of the time steps): R * THREADS consecutive rows owned by a block and
+// dealt round-robin (large plans), or R * 32 rows owned by one warp and dealt by ticket (small plans) -- see the kernel.
 // One thread per candidate; x / y / theta come back from the state planes through a cp.async ring, one step ahead.
 // Per step:
 //   * prediction cost: frx_pred_step -- 9.25 fp64 instructions per (candidate, obstacle) instead of 20, records read with
@@ -21,7 +22,7 @@
 //
 // Step chunks: neither term couples the steps of a candidate (the prediction cost is a sum, the sweep only wants the
 // FIRST hit), so a plan that would leave the GPU with one or two long units per warp -- 200,000 rows are 1.3 units per
-// resident warp -- is cut into C chunks of steps: C times more units of 1/C the length, dealt round-robin, each writes
+// resident warp -- is cut into C chunks of steps: C times more units of 1/C the length, each writes
 // its partial sum and its first hits to scratch, and frx_obstacle_finish_kernel adds them up in chunk order (fixed
 // order: the result does not depend on scheduling).  A chunk that starts at step i0 > 0 evaluates step i0 - 1 for the
 // ego box only (the hull of boxes i0 - 1, i0 needs it).  Plans with >= 8 units per warp run one chunk and finish inline.
