@@ -496,19 +496,36 @@ size_t frx_obstacle_scratch_elems(long long N) { return (size_t)8 * (size_t)N; }
 
 template <int PMODE, int THREADS, bool TICKET>
 static cudaError_t frx_launch_obstacle_shape(FrxKernelArgs& a, int sm_count, size_t stage_bytes, cudaStream_t st, int* launches) {
-    static thread_local int occ = 0, carve = -1;
+    // function attributes are sticky per function AND device: the cache is keyed by the device this launch goes to
+    struct Entry { int dev, occ, carve; };
+    static thread_local Entry cache[16];
+    static thread_local int n_cache = 0;
+    int dev = -1;
+    cudaGetDevice(&dev);
+    Entry* e = nullptr;
+    for (int k = 0; k < n_cache; ++k)
+        if (cache[k].dev == dev) { e = &cache[k]; break; }
+    if (e == nullptr) {
+        if (n_cache == 16) n_cache = 0;                     // more devices than slots: start over (attributes are set again)
+        e = &cache[n_cache++];
+        e->dev = dev; e->occ = 0; e->carve = -1;
+    }
     constexpr size_t RING = FRX_OBS_RING_BYTES(THREADS);
     constexpr size_t MAXDYN = RING + (PMODE == 0 ? (THREADS == 256 ? FRX_OBS_STAGE_BYTES_2 : FRX_OBS_STAGE_BYTES_1) : 0);
-    if (occ == 0) {
-        cudaFuncSetAttribute(frx_obstacle_kernel<PMODE, THREADS, TICKET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MAXDYN);
+    if (e->occ == 0) {
+        cudaError_t rc = cudaFuncSetAttribute(frx_obstacle_kernel<PMODE, THREADS, TICKET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MAXDYN);
+        if (rc != cudaSuccess) return rc;
+        int occ = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, frx_obstacle_kernel<PMODE, THREADS, TICKET>, THREADS, MAXDYN) != cudaSuccess || occ < 1) occ = 1;
+        e->occ = occ;
         if (getenv("FRX_DEBUG")) fprintf(stderr, "[frx] obstacle kernel<%d>: %d blocks of %d threads per SM\n", PMODE, occ, THREADS);
     }
+    const int occ = e->occ;
     const size_t dyn = RING + stage_bytes;
     const int want_carve = (int)(((512 / THREADS) * (dyn + 5 * 1024)) * 100 / (228 * 1024)) + 1;       // the rest stays L1
-    if (want_carve != carve) {
+    if (want_carve != e->carve) {
         cudaFuncSetAttribute(frx_obstacle_kernel<PMODE, THREADS, TICKET>, cudaFuncAttributePreferredSharedMemoryCarveout, want_carve > 100 ? 100 : want_carve);
-        carve = want_carve;
+        e->carve = want_carve;
     }
     const long long full = (long long)sm_count * occ;
     a.obs_chunks = frx_obstacle_chunks(a, full * (THREADS / 32));
