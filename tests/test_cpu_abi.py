@@ -66,3 +66,36 @@ def test_cpu_abi_grid_mode_equals_matrix_mode(cpu_lib):
     c = h.plan_grid(t1, v1, d1, x_cl, row_first=30, row_count=40)
     fc, _ = h.get_flags()
     assert np.array_equal(fc, fa[30:70]) and int(c.n_rows) == 40
+
+
+def test_planner_class_end_to_end_on_the_cpu_backend(cpu_lib):
+    """ReactivePlannerB200.plan() through the REAL ctypes binding (structs, result record, winner record, lazy read-backs)
+    with the CPU implementation of the ABI behind it: same selection, statistics and trajectory pair as with the
+    oracle-backed stand-in handler the drop-in tests use."""
+    from test_gpu_planner import make_planner
+    from oracle_handler import OracleHandler
+    from frenetix_motion_planner_b200 import ReactivePlannerB200
+    g, ref, prm, preds = load_golden("tjunction_draw")
+    outs = []
+    for handler in (_capi.Handler(0, library=cpu_lib), OracleHandler()):
+        orig = ReactivePlannerB200.__init__
+
+        def init(self, *a, **k):
+            k["handler"] = handler
+            orig(self, *a, **k)
+        ReactivePlannerB200.__init__ = init
+        try:
+            p = make_planner(g, prm, preds, 8.0)
+        finally:
+            ReactivePlannerB200.__init__ = orig
+        p.collision_check_enabled = True
+        p.obstacle_order = [100 + i for i in range(len(preds))]
+        pair = p.plan()
+        assert pair is not None and p.optimal_trajectory is not None
+        outs.append((p.optimal_trajectory.uniqueId, p.optimal_trajectory.cost, p._total_count, list(p._infeasible_count_kinematics),
+                     p.infeasible_kinematics_percentage, p.infeasible_count_collision,
+                     np.array([s.position for s in pair[0].state_list]), np.array(pair[2]), np.array(pair[3]),
+                     [t.uniqueId for t in p.all_traj[:40]]))
+    a, b = outs
+    assert a[0] == b[0] and a[1] == b[1] and a[2] == b[2] and a[3] == b[3] and a[4] == b[4] and a[5] == b[5]
+    assert np.array_equal(a[6], b[6]) and np.array_equal(a[7], b[7]) and np.array_equal(a[8], b[8]) and a[9] == b[9]
