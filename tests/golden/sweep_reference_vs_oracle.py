@@ -1,0 +1,85 @@
+"""Live differential sweep (build container only: needs /root/reference): the REFERENCE'S OWN code (the same entry points
+make_golden.py records, third-party imports stubbed) against the numpy oracle on RANDOM cases -- reference path kind and
+shape, Frenet state, speed regime, desired velocity, debug flags, obstacle sets -- with the assertions of
+tests/test_oracle_golden.py.  The committed goldens are 15 hand-picked cases; this widens the pin.
+
+    python tests/golden/sweep_reference_vs_oracle.py [n_cases] [first_seed]
+
+Prints one line per case and a summary; exit code 1 on any mismatch.  Nothing is written into the repository."""
+import os
+import sys
+import tempfile
+import time
+import traceback
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+import make_golden as mg  # noqa: E402  (installs the stubs, imports the reference)
+import helpers  # noqa: E402
+import test_oracle_golden as tog  # noqa: E402
+from frenetix_motion_planner_b200 import synthetic as syn  # noqa: E402
+
+
+def random_case(seed):
+    rng = np.random.default_rng(seed)
+    kind = int(rng.integers(0, 4))
+    poly = [syn.straight_polyline(260), syn.arc_polyline(R=float(rng.uniform(35, 300)), M=260),
+            syn.scurve_polyline(M=260, amp=float(rng.uniform(1, 6))),
+            syn.arc_polyline(R=float(rng.uniform(50, 200)), M=200, start_heading=float(rng.uniform(-1, 1)))][kind]
+    low = bool(rng.integers(0, 3) == 0)
+    v0 = float(rng.uniform(0.3, 1.9)) if low else float(rng.uniform(2.1, 14.0))
+    x_cl = ([float(rng.uniform(5, 40)), v0, float(rng.uniform(-2, 2))],
+            [float(rng.uniform(-1.5, 1.5)), float(rng.uniform(-0.3, 0.3)), float(rng.uniform(-0.2, 0.2))])
+    th0 = float(rng.uniform(-0.3, 0.3))
+    v_des = float(rng.uniform(0.5, 14.0))
+    draw, debug = bool(rng.integers(0, 2)), bool(rng.integers(0, 2))
+    n_obs = int(rng.integers(0, 7))
+    return dict(polyline=poly, x_cl=x_cl, v0=v0, th0=th0, v_des=v_des, draw=draw, debug=debug, n_obs=n_obs, seed=int(seed))
+
+
+def main():
+    n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 20
+    first = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
+    tmp = tempfile.mkdtemp(prefix="frx_sweep_")
+    mg.HERE = tmp                      # run_case writes ref_<name>.npz there
+    helpers.GOLDEN_DIR = tmp           # load_golden reads it back
+    bad = 0
+    t_all = time.time()
+    for k in range(n_cases):
+        c = random_case(first + k)
+        name = f"sweep{first + k}"
+        t0 = time.time()
+        try:
+            devnull = open(os.devnull, "w")
+            old = sys.stdout
+            sys.stdout = devnull
+            try:
+                mg.run_case(name, c["polyline"], c["x_cl"], c["v0"], c["th0"], c["v_des"], c["draw"], c["debug"], c["n_obs"],
+                            seed=c["seed"])
+            finally:
+                sys.stdout = old
+            tog.test_oracle_matches_reference_golden(name)
+            g = np.load(os.path.join(tmp, f"ref_{name}.npz"))
+            print(f"seed {first + k}: ok   rows {g['sampling'].shape[0]:4d} stored {int(g['stored'].sum()):4d} feasible {int(g['feasible'].sum()):4d} "
+                  f"optimal {int(g['optimal_id']):4d} low_vel {bool(g['low_vel_mode'])} draw {c['draw']} debug {c['debug']} obs {c['n_obs']} "
+                  f"({time.time() - t0:.1f} s)", flush=True)
+        except Exception:
+            bad += 1
+            print(f"seed {first + k}: MISMATCH {c}", flush=True)
+            traceback.print_exc()
+        finally:
+            try:
+                os.remove(os.path.join(tmp, f"ref_{name}.npz"))
+            except OSError:
+                pass
+    print(f"{n_cases - bad} of {n_cases} random cases: oracle == reference ({time.time() - t_all:.0f} s)")
+    return 1 if bad else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

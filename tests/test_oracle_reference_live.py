@@ -1,0 +1,19 @@
+"""Live pin of the numpy oracle (build container only): the reference's own code, imported unmodified from /root/reference
+under tests/golden/ref_stubs.py, against the oracle on RANDOM cases (tests/golden/sweep_reference_vs_oracle.py; a
+400-case run of that script is recorded in DESIGN.md section 4).  Skipped where the reference tree is absent (GPU box)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/frenetix_motion_planner"), reason="reference tree not present")
+def test_oracle_equals_the_reference_on_random_cases():
+    # its own process: the sweep installs import stubs and redirects the golden directory
+    out = subprocess.run([sys.executable, os.path.join(HERE, "golden", "sweep_reference_vs_oracle.py"), "8", "77000"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert "8 of 8 random cases: oracle == reference" in out.stdout
