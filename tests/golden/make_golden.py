@@ -94,16 +94,17 @@ FIELDS_CART = ("x", "y", "theta", "v", "a", "kappa", "kappa_dot")
 FIELDS_CL = ("s", "d", "theta", "s_dot", "s_ddot", "d_dot", "d_ddot")
 
 
-def run_case(name, polyline, x_cl, v0, th0, v_des, draw, debug, n_obs, cost_weights=None, seed=7, preds_list=None):
+def run_case(name, polyline, x_cl, v0, th0, v_des, draw, debug, n_obs, cost_weights=None, seed=7, preds_list=None,
+             samp_level=2, samp_max=3):
     cost_weights = cost_weights or syn.DEFAULT_COST_WEIGHTS
     Nt = 31
     if preds_list is None:
         preds_list = syn.synthetic_predictions(polyline, n_obs, 31, 0.1, seed) if n_obs else []
     n_obs = len(preds_list)
     predictions = {100 + i: p for i, p in enumerate(preds_list)}
-    pl = build_planner(polyline, x_cl, v0, th0, v_des, draw, debug, predictions, cost_weights)
+    pl = build_planner(polyline, x_cl, v0, th0, v_des, draw, debug, predictions, cost_weights, samp_max=samp_max)
 
-    bundle = pl._create_trajectory_bundle(x_cl[0], x_cl[1], pl.cost_function, samp_level=2)
+    bundle = pl._create_trajectory_bundle(x_cl[0], x_cl[1], pl.cost_function, samp_level=samp_level)
     trajs = list(bundle.trajectories)
     n = len(trajs)
     # sampling matrix in *generation order* (python set iteration order of the reference)
@@ -119,7 +120,7 @@ def run_case(name, polyline, x_cl, v0, th0, v_des, draw, debug, n_obs, cost_weig
         coeffs[r, 6:] = t.trajectory_lat.coeffs
     lat_delta_tau = np.array([t.trajectory_lat.delta_tau for t in trajs])
 
-    optimal = pl._get_optimal_trajectory(bundle, 2)
+    optimal = pl._get_optimal_trajectory(bundle, samp_level)
 
     in_list = np.zeros(n, bool); stored = np.zeros(n, bool)
     feasible = np.zeros(n, bool); valid = np.zeros(n, bool)

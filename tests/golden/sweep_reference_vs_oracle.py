@@ -39,7 +39,8 @@ def random_case(seed):
     v_des = float(rng.uniform(0.5, 14.0))
     draw, debug = bool(rng.integers(0, 2)), bool(rng.integers(0, 2))
     n_obs = int(rng.integers(0, 7))
-    return dict(polyline=poly, x_cl=x_cl, v0=v0, th0=th0, v_des=v_des, draw=draw, debug=debug, n_obs=n_obs, seed=int(seed))
+    level = int(rng.choice([1, 2, 2, 2, 3], p=[0.2, 0.25, 0.25, 0.25, 0.05]))      # 3 x 3 x 4 ... 17 x 17 x 18 end states per duration
+    return dict(polyline=poly, x_cl=x_cl, v0=v0, th0=th0, v_des=v_des, draw=draw, debug=debug, n_obs=n_obs, seed=int(seed), level=level)
 
 
 def main():
@@ -60,7 +61,7 @@ def main():
             sys.stdout = devnull
             try:
                 mg.run_case(name, c["polyline"], c["x_cl"], c["v0"], c["th0"], c["v_des"], c["draw"], c["debug"], c["n_obs"],
-                            seed=c["seed"])
+                            seed=c["seed"], samp_level=c["level"], samp_max=max(3, c["level"] + 1))
             finally:
                 sys.stdout = old
             tog.test_oracle_matches_reference_golden(name)
