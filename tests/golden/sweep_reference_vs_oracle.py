@@ -4,6 +4,7 @@ shape, Frenet state, speed regime, desired velocity, debug flags, obstacle sets 
 tests/test_oracle_golden.py.  The committed goldens are 15 hand-picked cases; this widens the pin.
 
     python tests/golden/sweep_reference_vs_oracle.py [n_cases] [first_seed]
+    python tests/golden/sweep_reference_vs_oracle.py --initial-states [n_poses] [first_seed]     (Frenet front end)
 
 Prints one line per case and a summary; exit code 1 on any mismatch.  Nothing is written into the repository."""
 import os
@@ -43,7 +44,45 @@ def random_case(seed):
     return dict(polyline=poly, x_cl=x_cl, v0=v0, th0=th0, v_des=v_des, draw=draw, debug=debug, n_obs=n_obs, seed=int(seed), level=level)
 
 
+def initial_state_sweep(n_poses, first):
+    """Planner._compute_initial_states of the reference (planner.py:567-635, unmodified, on make_golden's independent
+    projection) against ReactivePlannerB200._compute_initial_states on random paths and ego poses, both velocity modes."""
+    import types
+    from frenetix_motion_planner_b200.reactive_planner_b200 import ReactivePlannerB200
+    from frenetix_motion_planner_b200.coordinate_system import CoordinateSystem
+    bad = 0
+    worst = 0.0
+    t_all = time.time()
+    for k in range(n_poses):
+        rng = np.random.default_rng(first + k)
+        kind = int(rng.integers(0, 3))
+        poly = [syn.straight_polyline(120), syn.arc_polyline(R=float(rng.uniform(30, 300)), M=160),
+                syn.scurve_polyline(M=160, amp=float(rng.uniform(1, 6)))][kind]
+        cs = CoordinateSystem(poly)
+        s, d = rng.uniform(5.0, cs.ref_pos[-1] - 40.0), rng.uniform(-3.0, 3.0)
+        X = cs.convert_to_cartesian_coords(s, d)
+        i = int(np.argmax(cs.ref_pos > s)) - 1
+        low = bool(rng.integers(0, 3) == 0)
+        x_0 = types.SimpleNamespace(position=np.array(X), orientation=float(cs.ref_theta[i] + rng.uniform(-0.4, 0.4)),
+                                    velocity=float(rng.uniform(0.2, 1.9) if low else rng.uniform(2.1, 15.0)),
+                                    acceleration=float(rng.uniform(-3, 3)), yaw_rate=0.0,
+                                    steering_angle=float(rng.uniform(-0.3, 0.3)), time_step=0)
+        want = np.array(sum(mg.reference_initial_state(cs, x_0, low), []))
+        me = types.SimpleNamespace(coordinate_system=cs, vehicle_params=types.SimpleNamespace(**syn.VEHICLE_2), _LOW_VEL_MODE=low)
+        lon, lat = ReactivePlannerB200._compute_initial_states(me, x_0)
+        got = np.array(list(lon) + list(lat))
+        err = float(np.max(np.abs(got - want) / np.maximum(1.0, np.abs(want))))
+        worst = max(worst, err)
+        if not err <= 1e-9:
+            bad += 1
+            print(f"pose seed {first + k}: MISMATCH err {err:.3e} got {got} want {want}", flush=True)
+    print(f"{n_poses - bad} of {n_poses} random ego poses: Frenet initial state == reference (worst {worst:.2e}, {time.time() - t_all:.0f} s)")
+    return bad
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "--initial-states":
+        return 1 if initial_state_sweep(int(sys.argv[2]) if len(sys.argv) > 2 else 20, int(sys.argv[3]) if len(sys.argv) > 3 else 300) else 0
     n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 20
     first = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
     tmp = tempfile.mkdtemp(prefix="frx_sweep_")
