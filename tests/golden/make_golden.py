@@ -247,11 +247,11 @@ def refpath_cases():
     print("ref paths:", {k: v.shape for k, v in out.items() if k.endswith("_smooth")})
 
 
-def collision_probability_cases():
-    """get_collision_probability_fast of the reference (risk_assessment/collision_probability.py:141-261) on stored
-    trajectories -> ref_collision_probability.npz.  Two absent third-party calls are stood in for: scipy.stats.mvn.mvnun
-    (removed from scipy) by multivariate_normal.cdf(upper, lower_limit=lower), which evaluates the same rectangle
-    probability, and pycrcc.RectOBB (centre, half length, x axis) by a three-line class."""
+def collision_probability_module():
+    """The reference's risk_assessment.collision_probability with its two absent third-party calls stood in for:
+    scipy.stats.mvn.mvnun (removed from scipy) by multivariate_normal.cdf(upper, lower_limit=lower), which evaluates the same
+    rectangle probability, and pycrcc.RectOBB (centre, half length, x axis) by a three-line class."""
+
     import importlib
     from scipy.stats import multivariate_normal
     cp = importlib.import_module("risk_assessment.collision_probability")
@@ -275,6 +275,15 @@ def collision_probability_cases():
             return np.array([np.cos(self._o), np.sin(self._o)])
     cp.mvn = _Mvn
     cp.pycrcc = types.SimpleNamespace(RectOBB=_RectOBB)
+    return cp
+
+
+def collision_probability_cases():
+    """get_collision_probability_fast of the reference (risk_assessment/collision_probability.py:141-261) on stored
+    trajectories -> ref_collision_probability.npz.  Two absent third-party calls are stood in for: scipy.stats.mvn.mvnun
+    (removed from scipy) by multivariate_normal.cdf(upper, lower_limit=lower), which evaluates the same rectangle
+    probability, and pycrcc.RectOBB (centre, half length, x axis) by a three-line class."""
+    cp = collision_probability_module()
     veh = types.SimpleNamespace(**syn.VEHICLE_2)
     out = {}
     n_case = 0

@@ -5,6 +5,7 @@ tests/test_oracle_golden.py.  The committed goldens are 15 hand-picked cases; th
 
     python tests/golden/sweep_reference_vs_oracle.py [n_cases] [first_seed]
     python tests/golden/sweep_reference_vs_oracle.py --initial-states [n_poses] [first_seed]     (Frenet front end)
+    python tests/golden/sweep_reference_vs_oracle.py --collision-probability [n] [first_seed]   (cpp prediction cost)
 
 Prints one line per case and a summary; exit code 1 on any mismatch.  Nothing is written into the repository."""
 import os
@@ -80,7 +81,60 @@ def initial_state_sweep(n_poses, first):
     return bad
 
 
+def collision_probability_sweep(n_cases, first):
+    """get_collision_probability_fast of the reference (risk_assessment/collision_probability.py:141-261; scipy's rectangle
+    probability behind its mvn call) against the oracle's restatement with its own Genz bivariate-normal routine: random
+    ego trajectories, obstacles within a few metres of them, random correlations (all three |rho| branches of the algorithm),
+    now and then a zero covariance (the ground-truth case, :214-216)."""
+    import types
+    from oracle import frenet_oracle as fo
+    cp = mg.collision_probability_module()
+    veh = types.SimpleNamespace(**syn.VEHICLE_2)
+    bad, worst, nonzero = 0, 0.0, 0
+    t_all = time.time()
+    for k in range(n_cases):
+        rng = np.random.default_rng(first + k)
+        n = int(rng.integers(8, 32))
+        t = np.arange(n) * 0.1
+        v, yaw_rate, th0 = rng.uniform(0.5, 14.0), rng.uniform(-0.3, 0.3), rng.uniform(-3.1, 3.1)
+        th = th0 + yaw_rate * t
+        x = rng.uniform(-50, 50) + np.cumsum(v * 0.1 * np.cos(th))
+        y = rng.uniform(-50, 50) + np.cumsum(v * 0.1 * np.sin(th))
+        preds = {}
+        for o in range(int(rng.integers(1, 5))):
+            m = int(rng.integers(4, n + 3))
+            off = rng.uniform(-6, 6, 2)
+            j = np.minimum(np.arange(m), n - 1)
+            pos = np.stack([x[j], y[j]], axis=1) + off + rng.normal(0, 0.4, (m, 2))
+            cov = np.zeros((m, 2, 2))
+            for q in range(m):
+                rho = float(rng.choice([0.0, rng.uniform(-0.29, 0.29), rng.uniform(0.3, 0.74), -rng.uniform(0.3, 0.74),
+                                        rng.uniform(0.75, 0.92), rng.uniform(0.93, 0.995), -rng.uniform(0.93, 0.995)]))
+                sx, sy = rng.uniform(0.1, 1.5), rng.uniform(0.1, 1.5)
+                cov[q] = [[sx * sx, rho * sx * sy], [rho * sx * sy, sy * sy]]
+                if rng.integers(0, 12) == 0:
+                    cov[q] = 0.0
+            preds[100 + o] = {"pos_list": pos, "cov_list": cov, "orientation_list": rng.uniform(-3.1, 3.1, m),
+                              "shape": {"length": float(rng.uniform(3, 6)), "width": float(rng.uniform(1.5, 2.5))}}
+        traj = types.SimpleNamespace(cartesian=types.SimpleNamespace(x=x, y=y, theta=th))
+        want = cp.get_collision_probability_fast(traj, preds, veh)
+        got = fo.collision_probability_fast(x, y, th, list(preds.values()), veh.length, veh.width)
+        for o, oid in enumerate(preds):
+            w = np.asarray(want[oid])
+            err = float(np.abs(got[o] - w).max()) if got[o].shape == w.shape else float("inf")
+            worst = max(worst, err)
+            nonzero += int((w > 0).sum())
+            if not err < 1e-12:
+                bad += 1
+                print(f"collision-probability seed {first + k} obstacle {o}: MISMATCH err {err:.3e}", flush=True)
+    print(f"{n_cases} random trajectories, {nonzero} non-zero step probabilities: {'all equal' if not bad else str(bad) + ' MISMATCHES'} "
+          f"(worst {worst:.2e}, {time.time() - t_all:.0f} s)")
+    return bad
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "--collision-probability":
+        return 1 if collision_probability_sweep(int(sys.argv[2]) if len(sys.argv) > 2 else 20, int(sys.argv[3]) if len(sys.argv) > 3 else 700) else 0
     if len(sys.argv) > 1 and sys.argv[1] == "--initial-states":
         return 1 if initial_state_sweep(int(sys.argv[2]) if len(sys.argv) > 2 else 20, int(sys.argv[3]) if len(sys.argv) > 3 else 300) else 0
     n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 20

@@ -25,3 +25,11 @@ def test_frenet_initial_state_equals_the_reference_on_random_poses():
                          capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "6 of 6 random ego poses: Frenet initial state == reference" in out.stdout
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/frenetix_motion_planner"), reason="reference tree not present")
+def test_collision_probability_equals_the_reference_on_random_cases():
+    out = subprocess.run([sys.executable, os.path.join(HERE, "golden", "sweep_reference_vs_oracle.py"), "--collision-probability", "200", "99000"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert "all equal" in out.stdout
