@@ -6,6 +6,7 @@ tests/test_oracle_golden.py.  The committed goldens are 15 hand-picked cases; th
     python tests/golden/sweep_reference_vs_oracle.py [n_cases] [first_seed]
     python tests/golden/sweep_reference_vs_oracle.py --initial-states [n_poses] [first_seed]     (Frenet front end)
     python tests/golden/sweep_reference_vs_oracle.py --collision-probability [n] [first_seed]   (cpp prediction cost)
+    python tests/golden/sweep_reference_vs_oracle.py --sampling-order [n] [first_seed]          (level sets and their order, a1)
 
 Prints one line per case and a summary; exit code 1 on any mismatch.  Nothing is written into the repository."""
 import os
@@ -132,7 +133,43 @@ def collision_probability_sweep(n_cases, first):
     return bad
 
 
+def sampling_order_sweep(n_cases, first):
+    """Level sets of the reference's SamplingHandler (sampling_matrix.py:17-195) and their ITERATION ORDER (python set order:
+    it fixes uniqueId = row index and how equal-cost ties break) against the package's handler + sampling_axes, python and
+    cpp style, for random v / d / t configurations and every level."""
+    from frenetix_motion_planner_b200.sampling_matrix import SamplingHandler as OurHandler, sampling_axes
+    bad = 0
+    for k in range(n_cases):
+        rng = np.random.default_rng(first + k)
+        v_lo = float(np.round(rng.uniform(0.001, 8.0), int(rng.integers(1, 6))))
+        v_hi = v_lo + float(np.round(rng.uniform(0.5, 20.0), int(rng.integers(1, 6))))
+        d_half = float(rng.choice([3.0, 2.5, 1.75, 4.0, float(np.round(rng.uniform(1, 5), 2))]))
+        t_min = float(rng.choice([1.1, 0.9, 0.5, 1.5]))
+        horizon = float(rng.choice([3.0, 5.0, 4.0, 2.0]))
+        levels = int(rng.integers(3, 6))
+        kw = dict(dt=0.1, max_sampling_number=levels, t_min=t_min, horizon=horizon, delta_d_max=d_half, delta_d_min=-d_half, d_ego_pos=False)
+        ref, our = mg.SamplingHandler(**kw), OurHandler(**kw)
+        ref.set_v_sampling(v_lo, v_hi); our.set_v_sampling(v_lo, v_hi)
+        d0, ss0 = float(rng.uniform(-1, 1)), float(rng.uniform(v_lo, v_hi))
+        x_cl = ([3.0, ss0, 0.0], [d0, 0.0, 0.0])
+        N = int(horizon / 0.1)
+        for lvl in range(levels):
+            t, v, d = sampling_axes(our, lvl, x_cl)
+            tc, vc, dc = sampling_axes(our, lvl, x_cl, cpp_style=True)
+            ok = (list(t) == list(ref.t_sampling.to_range(lvl)) and list(v) == list(ref.v_sampling.to_range(lvl))
+                  and list(d) == list(ref.d_sampling.to_range(lvl).union({d0}))
+                  and list(tc) == list(ref.t_sampling.to_range(lvl).union({N * 0.1}))
+                  and list(vc) == list(ref.v_sampling.to_range(lvl).union({ss0})))
+            if not ok:
+                bad += 1
+                print(f"sampling seed {first + k} level {lvl}: MISMATCH", flush=True)
+    print(f"{n_cases} random sampling configurations x every level: {'all equal' if not bad else str(bad) + ' MISMATCHES'}")
+    return bad
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "--sampling-order":
+        return 1 if sampling_order_sweep(int(sys.argv[2]) if len(sys.argv) > 2 else 200, int(sys.argv[3]) if len(sys.argv) > 3 else 900) else 0
     if len(sys.argv) > 1 and sys.argv[1] == "--collision-probability":
         return 1 if collision_probability_sweep(int(sys.argv[2]) if len(sys.argv) > 2 else 20, int(sys.argv[3]) if len(sys.argv) > 3 else 700) else 0
     if len(sys.argv) > 1 and sys.argv[1] == "--initial-states":
