@@ -7,6 +7,7 @@ tests/test_oracle_golden.py.  The committed goldens are 15 hand-picked cases; th
     python tests/golden/sweep_reference_vs_oracle.py --initial-states [n_poses] [first_seed]     (Frenet front end)
     python tests/golden/sweep_reference_vs_oracle.py --collision-probability [n] [first_seed]   (cpp prediction cost)
     python tests/golden/sweep_reference_vs_oracle.py --sampling-order [n] [first_seed]          (level sets and their order, a1)
+    python tests/golden/sweep_reference_vs_oracle.py --refpath [n] [first_seed]                 (reference-path preparation, 8f-2)
 
 Prints one line per case and a summary; exit code 1 on any mismatch.  Nothing is written into the repository."""
 import os
@@ -167,7 +168,44 @@ def sampling_order_sweep(n_cases, first):
     return bad
 
 
+def refpath_sweep(n_cases, first):
+    """extend_ref_path_both_ends / smooth_ref_path of the reference (utils_coordinate_system.py:20-58,110-134) against
+    frenetix_motion_planner_b200.reference_path on random dense centre lines.  (commonroad_dc's resample_polyline is
+    absent: both sides use the package's resampler, as in make_golden.refpath_cases -- the extension, the chaikin
+    smoothing and the spline pipeline around it are the reference's.)"""
+    import importlib
+    import commonroad_dc.geometry.util as cdc_util                 # stub module
+    from frenetix_motion_planner_b200 import reference_path as rp
+    cdc_util.resample_polyline = rp.resample_polyline
+    ucs = importlib.import_module("cr_scenario_handler.utils.utils_coordinate_system")
+    ucs.resample_polyline = rp.resample_polyline
+    bad, worst = 0, 0.0
+    for k in range(n_cases):
+        rng = np.random.default_rng(first + k)
+        kind = int(rng.integers(0, 3))
+        raw = [syn.arc_polyline(R=float(rng.uniform(25, 200)), M=int(rng.integers(60, 160)), start_heading=float(rng.uniform(-3, 3))),
+               syn.scurve_polyline(M=int(rng.integers(120, 260)), amp=float(rng.uniform(1, 8))),
+               syn.straight_polyline(int(rng.integers(60, 200)))][kind]
+        if kind == 2:                                              # a straight line with a gentle random wobble
+            raw = raw + np.stack([np.zeros(len(raw)), np.cumsum(rng.normal(0, 0.02, len(raw)))], axis=1)
+        route = rp.resample_polyline(raw, float(rng.choice([0.125, 0.25, 0.5])))
+        ext_r, ext_o = ucs.extend_ref_path_both_ends(route), rp.extend_ref_path_both_ends(route)
+        ok = np.array_equal(ext_r, ext_o)
+        far = float(rng.choice([30, 80, 120]))
+        ok = ok and np.array_equal(ucs.extend_ref_path_both_ends(route, far), rp.extend_ref_path_both_ends(route, far))
+        sm_r, sm_o = ucs.smooth_ref_path(ext_r), rp.smooth_ref_path(ext_o)
+        err = float(np.abs(sm_r - sm_o).max()) if sm_r.shape == sm_o.shape else float("inf")
+        worst = max(worst, err)
+        if not (ok and err <= 1e-10):
+            bad += 1
+            print(f"refpath seed {first + k}: MISMATCH extended_equal {ok} smooth err {err:.3e}", flush=True)
+    print(f"{n_cases} random centre lines: {'all equal' if not bad else str(bad) + ' MISMATCHES'} (smoothed path: worst {worst:.2e} m)")
+    return bad
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "--refpath":
+        return 1 if refpath_sweep(int(sys.argv[2]) if len(sys.argv) > 2 else 50, int(sys.argv[3]) if len(sys.argv) > 3 else 1200) else 0
     if len(sys.argv) > 1 and sys.argv[1] == "--sampling-order":
         return 1 if sampling_order_sweep(int(sys.argv[2]) if len(sys.argv) > 2 else 200, int(sys.argv[3]) if len(sys.argv) > 3 else 900) else 0
     if len(sys.argv) > 1 and sys.argv[1] == "--collision-probability":

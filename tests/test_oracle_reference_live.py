@@ -41,3 +41,11 @@ def test_level_sets_and_their_order_equal_the_reference_on_random_configurations
                          capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "all equal" in out.stdout
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/frenetix_motion_planner"), reason="reference tree not present")
+def test_reference_path_preparation_equals_the_reference_on_random_centre_lines():
+    out = subprocess.run([sys.executable, os.path.join(HERE, "golden", "sweep_reference_vs_oracle.py"), "--refpath", "40", "93000"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert "all equal" in out.stdout
