@@ -8,6 +8,7 @@ tests/test_oracle_golden.py.  The committed goldens are 15 hand-picked cases; th
     python tests/golden/sweep_reference_vs_oracle.py --collision-probability [n] [first_seed]   (cpp prediction cost)
     python tests/golden/sweep_reference_vs_oracle.py --sampling-order [n] [first_seed]          (level sets and their order, a1)
     python tests/golden/sweep_reference_vs_oracle.py --refpath [n] [first_seed]                 (reference-path preparation, 8f-2)
+    python tests/golden/sweep_reference_vs_oracle.py --trajectory-pair [n] [first_seed]         (output conversion of plan(), a13)
 
 Prints one line per case and a summary; exit code 1 on any mismatch.  Nothing is written into the repository."""
 import os
@@ -203,7 +204,70 @@ def refpath_sweep(n_cases, first):
     return bad
 
 
+def trajectory_pair_sweep(n_cases, first):
+    """Planner._compute_trajectory_pair + shift_orientation of the reference (planner.py:394-447,536-542) -- what every caller
+    of plan() consumes -- against ReactivePlannerB200._compute_trajectory_pair on random selected trajectories (oracle states of
+    random cases), random x_0 time step / yaw rate / orientation (incl. orientations that force the 2 pi shift).  commonroad's
+    state / trajectory containers are absent: the reference function fills plain attribute bags instead."""
+    import types
+    import importlib
+    from oracle import frenet_oracle as fo
+    from frenetix_motion_planner_b200.reactive_planner_b200 import ReactivePlannerB200
+    from frenetix_motion_planner_b200.coordinate_system import CoordinateSystem
+    pl = importlib.import_module("frenetix_motion_planner.planner")
+
+    class Bag(types.SimpleNamespace):
+        pass
+    pl.ReactivePlannerState = pl.CustomState = Bag
+    pl.Trajectory = lambda t0, states: types.SimpleNamespace(initial_time_step=t0, state_list=states)
+    bad, worst = 0, 0.0
+    for k in range(n_cases):
+        c = random_case(first + k)
+        rng = np.random.default_rng(first + k + 7)
+        cs = CoordinateSystem(c["polyline"])
+        ref = fo.RefPath(cs.ref_pos, cs.ref_theta, cs.ref_curv, cs.ref_curv_d, np.ascontiguousarray(c["polyline"][:, 0]),
+                         np.ascontiguousarray(c["polyline"][:, 1]))
+        prm = fo.Params(low_vel_mode=c["v0"] < 2.0, x0_orientation=c["th0"], desired_velocity=c["v_des"], draw_traj_set=True,
+                        **{q: syn.VEHICLE_2[q] for q in ("a_max", "v_switch", "delta_max", "wheelbase", "wb_rear_axle", "length", "width")})
+        v_lo, v_hi = syn.velocity_interval(c["v0"], syn.VEHICLE_2["a_max"], 3.0, syn.VEHICLE_2["v_max"])
+        S = syn.grid_sampling_matrix(np.array([1.1, 2.0, 3.0]), np.linspace(v_lo, v_hi, 3), np.linspace(-3, 3, 4), c["x_cl"])
+        out = fo.plan(S, ref, prm, [], collision_check=False)
+        stored = np.flatnonzero((out["flags"] & fo.FLAG_STORED) != 0)
+        for r in stored[:: max(1, len(stored) // 4)]:
+            st = out["states"][:, r, :]
+            traj = types.SimpleNamespace(
+                cartesian=types.SimpleNamespace(x=st[0], y=st[1], theta=st[2], v=st[3], a=st[4], kappa=st[5], kappa_dot=st[6]),
+                curvilinear=types.SimpleNamespace(s=st[7], d=st[8], theta=st[9], s_dot=st[10], s_ddot=st[11], d_dot=st[12], d_ddot=st[13]))
+            x_0 = types.SimpleNamespace(time_step=int(rng.integers(0, 200)), yaw_rate=float(rng.uniform(-0.5, 0.5)),
+                                        orientation=float(st[2][0] + rng.choice([0.0, 0.1, 2 * np.pi, -2 * np.pi, 3.0, -3.0])))
+            veh = types.SimpleNamespace(**syn.VEHICLE_2)
+            me = types.SimpleNamespace(x_0=x_0, dT=0.1, vehicle_params=veh)
+            me.shift_orientation = lambda *a, **kw: pl.Planner.shift_orientation(me, *a, **kw)
+            want = pl.Planner._compute_trajectory_pair(me, traj)
+            me2 = types.SimpleNamespace(x_0=x_0, dT=0.1, vehicle_params=veh)
+            got = ReactivePlannerB200._compute_trajectory_pair(me2, traj)
+            ok = len(got[0].state_list) == len(want[0].state_list) and got[0].initial_time_step == want[0].initial_time_step
+            for a, b in zip(got[0].state_list, want[0].state_list):
+                for f in ("time_step", "orientation", "velocity", "acceleration", "yaw_rate", "steering_angle"):
+                    ok = ok and (getattr(a, f) == getattr(b, f))
+                    if isinstance(getattr(b, f), float) and getattr(a, f) != getattr(b, f):
+                        worst = max(worst, abs(getattr(a, f) - getattr(b, f)))
+                ok = ok and np.array_equal(a.position, b.position)
+            for a, b in zip(got[1].state_list, want[1].state_list):
+                for f in ("time_step", "velocity", "acceleration", "orientation", "yaw_rate"):
+                    ok = ok and (getattr(a, f) == getattr(b, f))
+                ok = ok and np.array_equal(a.position, b.position)
+            ok = ok and np.array_equal(np.array(got[2]), np.array(want[2])) and np.array_equal(np.array(got[3]), np.array(want[3]))
+            if not ok:
+                bad += 1
+                print(f"trajectory pair seed {first + k} row {r}: MISMATCH (worst scalar difference so far {worst:.3e})", flush=True)
+    print(f"{n_cases} random cases x 4 trajectories: {'all equal' if not bad else str(bad) + ' MISMATCHES'}")
+    return bad
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "--trajectory-pair":
+        return 1 if trajectory_pair_sweep(int(sys.argv[2]) if len(sys.argv) > 2 else 50, int(sys.argv[3]) if len(sys.argv) > 3 else 1500) else 0
     if len(sys.argv) > 1 and sys.argv[1] == "--refpath":
         return 1 if refpath_sweep(int(sys.argv[2]) if len(sys.argv) > 2 else 50, int(sys.argv[3]) if len(sys.argv) > 3 else 1200) else 0
     if len(sys.argv) > 1 and sys.argv[1] == "--sampling-order":

@@ -49,3 +49,11 @@ def test_reference_path_preparation_equals_the_reference_on_random_centre_lines(
                          capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "all equal" in out.stdout
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/frenetix_motion_planner"), reason="reference tree not present")
+def test_trajectory_pair_equals_the_reference_on_random_trajectories():
+    out = subprocess.run([sys.executable, os.path.join(HERE, "golden", "sweep_reference_vs_oracle.py"), "--trajectory-pair", "60", "95000"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert "all equal" in out.stdout
