@@ -9,6 +9,7 @@ tests/test_oracle_golden.py.  The committed goldens are 15 hand-picked cases; th
     python tests/golden/sweep_reference_vs_oracle.py --sampling-order [n] [first_seed]          (level sets and their order, a1)
     python tests/golden/sweep_reference_vs_oracle.py --refpath [n] [first_seed]                 (reference-path preparation, 8f-2)
     python tests/golden/sweep_reference_vs_oracle.py --trajectory-pair [n] [first_seed]         (output conversion of plan(), a13)
+    python tests/golden/sweep_reference_vs_oracle.py --inactive-costs [n] [first_seed]          (the five optional cost terms, a9)
 
 Prints one line per case and a summary; exit code 1 on any mismatch.  Nothing is written into the repository."""
 import os
@@ -265,7 +266,42 @@ def trajectory_pair_sweep(n_cases, first):
     return bad
 
 
+def inactive_cost_sweep(n_cases, first):
+    """The five cost terms that are inactive by default but implemented on the device (acceleration, jerk, orientation_offset,
+    path_length, distance_to_obstacles: partial_cost_functions.py:24-46,141-151,172-196) -- the reference's functions on
+    random samples of random length against the oracle's restatement."""
+    import types
+    from oracle import frenet_oracle as fo
+    bad, worst = 0, 0.0
+    for k in range(n_cases):
+        rng = np.random.default_rng(first + k)
+        Nt = int(rng.integers(6, 64))
+        a = rng.normal(0, 2, Nt); v = np.abs(rng.normal(8, 3, Nt)); th = rng.normal(0, 0.3, Nt)
+        x = np.cumsum(v) * 0.1 + rng.uniform(-100, 100); y = rng.normal(0, 2, Nt) + rng.uniform(-100, 100)
+        traj = types.SimpleNamespace(dt=0.1, cartesian=types.SimpleNamespace(a=a, v=v, x=x, y=y), curvilinear=types.SimpleNamespace(theta=th))
+        obs_pos = np.stack([x[rng.integers(0, Nt, 3)] + rng.normal(0, 6, 3), y[rng.integers(0, Nt, 3)] + rng.normal(0, 6, 3)], axis=1)
+        scen = types.SimpleNamespace(obstacles=[types.SimpleNamespace(state_at_time=lambda t, p=p: types.SimpleNamespace(position=p)) for p in obs_pos])
+        planner = types.SimpleNamespace(x_0=types.SimpleNamespace(time_step=0))
+        want = {"acceleration": mg.pcf.acceleration_costs(traj), "jerk": mg.pcf.jerk_costs(traj),
+                "orientation_offset": mg.pcf.orientation_offset_costs(traj), "path_length": mg.pcf.path_length_costs(traj),
+                "distance_to_obstacles": mg.pcf.distance_to_obstacles_costs(traj, planner=planner, scenario=scen)}
+        st = np.zeros((14, Nt))
+        st[fo.F_A], st[fo.F_V], st[fo.F_THETA_CL], st[fo.F_X], st[fo.F_Y] = a, v, th, x, y
+        prm = fo.Params(N=Nt - 1, obstacle_positions=obs_pos)
+        for name, w in want.items():
+            got = fo._costs_for(name, st, None, None, prm, [], [], Nt)
+            err = abs(float(got) - float(w)) / max(1.0, abs(float(w)))
+            worst = max(worst, err)
+            if not err < 1e-12:
+                bad += 1
+                print(f"cost seed {first + k} {name}: MISMATCH {got} vs {w}", flush=True)
+    print(f"{n_cases} random samples x 5 cost terms: {'all equal' if not bad else str(bad) + ' MISMATCHES'} (worst {worst:.2e})")
+    return bad
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "--inactive-costs":
+        return 1 if inactive_cost_sweep(int(sys.argv[2]) if len(sys.argv) > 2 else 200, int(sys.argv[3]) if len(sys.argv) > 3 else 3000) else 0
     if len(sys.argv) > 1 and sys.argv[1] == "--trajectory-pair":
         return 1 if trajectory_pair_sweep(int(sys.argv[2]) if len(sys.argv) > 2 else 50, int(sys.argv[3]) if len(sys.argv) > 3 else 1500) else 0
     if len(sys.argv) > 1 and sys.argv[1] == "--refpath":

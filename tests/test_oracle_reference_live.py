@@ -117,3 +117,11 @@ print("planner methods equal")
 '''
     out = subprocess.run([sys.executable, "-c", code, os.path.join(HERE, "golden"), os.path.dirname(HERE)], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "planner methods equal" in out.stdout, out.stdout[-2000:] + out.stderr[-3000:]
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/frenetix_motion_planner"), reason="reference tree not present")
+def test_optional_cost_terms_equal_the_reference_on_random_samples():
+    out = subprocess.run([sys.executable, os.path.join(HERE, "golden", "sweep_reference_vs_oracle.py"), "--inactive-costs", "300", "97000"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert "all equal" in out.stdout
