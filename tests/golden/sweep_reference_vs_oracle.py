@@ -46,7 +46,14 @@ def random_case(seed):
     draw, debug = bool(rng.integers(0, 2)), bool(rng.integers(0, 2))
     n_obs = int(rng.integers(0, 7))
     level = int(rng.choice([1, 2, 2, 2, 3], p=[0.2, 0.25, 0.25, 0.25, 0.05]))      # 3 x 3 x 4 ... 17 x 17 x 18 end states per duration
-    return dict(polyline=poly, x_cl=x_cl, v0=v0, th0=th0, v_des=v_des, draw=draw, debug=debug, n_obs=n_obs, seed=int(seed), level=level)
+    weights = None
+    if rng.integers(0, 3) == 0:        # other weights, and the optional terms switched on (cost_function.py:55-91 picks up w > 0)
+        weights = {k: float(np.round(w * rng.uniform(0.2, 3.0), 3)) for k, w in syn.DEFAULT_COST_WEIGHTS.items()}
+        for k in ("acceleration", "jerk", "orientation_offset", "path_length"):
+            if rng.integers(0, 2):
+                weights[k] = float(np.round(rng.uniform(0.01, 2.0), 3))
+    return dict(polyline=poly, x_cl=x_cl, v0=v0, th0=th0, v_des=v_des, draw=draw, debug=debug, n_obs=n_obs, seed=int(seed), level=level,
+                weights=weights)
 
 
 def initial_state_sweep(n_poses, first):
@@ -329,13 +336,13 @@ def main():
             sys.stdout = devnull
             try:
                 mg.run_case(name, c["polyline"], c["x_cl"], c["v0"], c["th0"], c["v_des"], c["draw"], c["debug"], c["n_obs"],
-                            seed=c["seed"], samp_level=c["level"], samp_max=max(3, c["level"] + 1))
+                            seed=c["seed"], samp_level=c["level"], samp_max=max(3, c["level"] + 1), cost_weights=c["weights"])
             finally:
                 sys.stdout = old
             tog.test_oracle_matches_reference_golden(name)
             g = np.load(os.path.join(tmp, f"ref_{name}.npz"))
             print(f"seed {first + k}: ok   rows {g['sampling'].shape[0]:4d} stored {int(g['stored'].sum()):4d} feasible {int(g['feasible'].sum()):4d} "
-                  f"optimal {int(g['optimal_id']):4d} low_vel {bool(g['low_vel_mode'])} draw {c['draw']} debug {c['debug']} obs {c['n_obs']} "
+                  f"optimal {int(g['optimal_id']):4d} low_vel {bool(g['low_vel_mode'])} draw {c['draw']} debug {c['debug']} obs {c['n_obs']} terms {len(g['cost_names'])} "
                   f"({time.time() - t0:.1f} s)", flush=True)
         except Exception:
             bad += 1
